@@ -1,0 +1,79 @@
+"""
+ctypes binding of libhaptools_cuda.so (include/haptools_cuda.h) -- the C-ABI boundary of the
+haplotype-transform hot path.  There is NO CPU fallback: if the library is missing or was
+built against another ABI version, importing a symbol from here raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libhaptools_cuda.so"
+ABI_VERSION = 4
+
+HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
+HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
+HT_PACK_AUTO, HT_PACK_GENERIC, HT_PACK_VARIANT_MAJOR, HT_PACK_SAMPLE_MAJOR = 0, 1, 2, 3
+HT_COPY_H2D, HT_COPY_D2H, HT_COPY_D2D = 1, 2, 3
+TILE_SAMPLES = 1024
+RECORD_BYTES = 256
+
+_p, _i64, _i32, _u32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/haptools_cuda.h declares
+SIGNATURES = {
+    "ht_version": (_i32, []),
+    "ht_last_error": (C.c_char_p, []),
+    "ht_num_tiles": (_i64, [_i64]),
+    "ht_plane_bytes": (_sz, [_i64, _i64]),
+    "ht_pack_u8": (
+        _i32,
+        [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i32, _p],
+    ),
+    "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p]),
+    "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "ht_count_bits": (_i32, [_p, _i64, _i64, _p, _p]),
+    "ht_synth_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _p]),
+    "ht_synth_ancestry": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _u32, _u32, _p]),
+    "ht_copy2d": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i32, _p]),
+    "ht_host_register": (_i32, [_p, _sz]),
+    "ht_host_unregister": (_i32, [_p]),
+}
+
+_lib = None
+
+
+class HaptoolsCudaError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """The loaded library (loaded once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise HaptoolsCudaError(
+                f"{LIB_PATH} is missing: build it with `python -m haptools_b200._cuda.build` "
+                "(there is no CPU fallback for the transform)"
+            )
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        got = handle.ht_version()
+        if got != ABI_VERSION:
+            raise HaptoolsCudaError(f"libhaptools_cuda ABI {got} != expected {ABI_VERSION}: rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a non-zero return code into the exception class the Python API documents."""
+    if rc == HT_OK:
+        return
+    msg = lib().ht_last_error().decode("utf-8", "replace")
+    if rc == HT_ERR_BAD_ARG:
+        raise ValueError(f"{what}: {msg}")
+    raise HaptoolsCudaError(f"{what}: {msg} (code {rc})")

@@ -1,0 +1,81 @@
+"""
+Builds haptools_b200/_cuda/libhaptools_cuda.so from haptools_b200/csrc/*.cu with nvcc for
+sm_100a (B200).  In-tree on purpose: the .so is git-ignored but travels with the repo
+snapshot to the GPU box.
+
+    python -m haptools_b200._cuda.build [--force]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent.parent
+REPO = PKG.parent
+CSRC = PKG / "csrc"
+INCLUDE = REPO / "include"
+LIB_PATH = Path(__file__).resolve().parent / "libhaptools_cuda.so"
+SOURCES = ["ht_capi.cu", "ht_pack.cu", "ht_transform.cu", "ht_synth.cu"]
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-lineinfo",
+    "-std=c++17",
+    "--use_fast_math",
+    "-Xcompiler",
+    "-fPIC,-O2,-Wall",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        raise RuntimeError("nvcc not found: cannot build libhaptools_cuda.so")
+    return nvcc
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    built = LIB_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    return any(d.stat().st_mtime > built for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile and link the shared library; returns its path."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objdir = REPO / "build"
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = objdir / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, proc in procs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out:
+            print(out, file=sys.stderr)
+        objs.append(str(obj))
+    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs, "--cudart", "static"]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}")
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

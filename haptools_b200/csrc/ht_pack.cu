@@ -1,0 +1,487 @@
+// K1 -- pack (sm_100a): genotype bytes -> per-key bit-planes over samples.
+//
+// Replaces, without materialising either of them,
+//   * the column gather `gts.subset(variants=...)`            haptools/data/haplotypes.py:1388
+//                                                             -> haptools/data/genotypes.py:440
+//   * `np.equal(allele_arr, gts.data[:, :, :2])`              haptools/data/haplotypes.py:1404
+//                                                             haptools/transform.py:137
+//   * `gts.ancestry[:, idxs[i]] == ancestries[i]`             haptools/transform.py:146
+//     (folded into the key: bit = GT==allele && ANC==label)
+//
+// Plane layout (include/haptools_cuda.h): planes[tile][key][word 0..31][strand 0..1] uint32,
+// tile = 1024 samples, bit b of word w = sample tile*1024 + 32*w + b, bits of samples >= n
+// are 0.  A (tile, key) record is 256 contiguous bytes -- what one warp of the transform
+// kernel reads per key.
+//
+// Three kernels, chosen from the strides of the genotype array:
+//   generic        any strides, uint8 or pgenlib int32: byte loads + __ballot_sync
+//   variant-major  samples contiguous (VCF reader layout): 128-bit coalesced loads, SWAR byte
+//                  compare, carry-free multiply to gather match bits, 4-lane shuffle merge
+//   sample-major   variants contiguous (PGEN reader layout / C-contiguous arrays): each thread
+//                  streams 8-byte column chunks down 128 sample rows, accumulating match
+//                  bits bytewise (acc = acc>>1 | flags), then byte-transposes with PRMT
+//
+// Roofline: HBM read of n*V*2 genotype bytes (+ ancestry) and write of A*2*ceil(n/32)*4.
+#include "ht_common.cuh"
+
+namespace ht {
+
+constexpr int kPackWarps = 8;
+constexpr int kPackThreads = kPackWarps * 32;
+constexpr int kSmCols = 128;  // columns per CTA of the sample-major kernel
+
+struct PackArgs {
+    const uint8_t* gt;
+    int64_t gs, gv, gc;  // byte strides: sample, variant, strand
+    const uint8_t* anc;
+    int64_t as, av, ac;
+    int64_t n;  // samples
+    const uint32_t* var_col;
+    const uint32_t* var_key_off;
+    const uint8_t* key_allele;
+    const uint8_t* key_label;
+    const int32_t* col_var;  // dense column -> variant map (sample-major kernel)
+    int64_t n_cols;
+    int64_t n_vars;
+    int64_t n_keys;     // record pitch of the plane workspace (total keys)
+    int64_t key_base;   // added to var_key_off-relative key ids (chunked int32 packing)
+    uint32_t* planes;
+    uint32_t* flags;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    return __byte_perm(a, b, sel);
+}
+
+// flags at bit 7 of each byte -> the 4 flags as a nibble (byte 0 -> bit 0)
+__device__ __forceinline__ uint32_t nib(uint32_t f) { return (f * 0x00204081u) >> 28; }
+
+// 0x80 in every byte that is non-zero
+__device__ __forceinline__ uint32_t nz_bytes_msb(uint32_t x) {
+    return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+
+// QC side channel: HT_FLAG_MISSING if some byte >= 254, HT_FLAG_NON_BIALLELIC if some byte in
+// 2..253 (Genotypes.check_missing / check_biallelic, haptools/data/genotypes.py:444-528)
+__device__ __forceinline__ uint32_t qc_flags4(uint32_t x) {
+    const uint32_t miss = eq_bytes_msb(x | 0x01010101u, 0xffffffffu);
+    const uint32_t hi = nz_bytes_msb(x & 0xfefefefeu) & ~miss;
+    return (miss ? HT_FLAG_MISSING : 0u) | (hi ? HT_FLAG_NON_BIALLELIC : 0u);
+}
+
+__device__ __forceinline__ void publish_flags(uint32_t* flags, uint32_t f) {
+    if (!flags) return;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+// mask of the samples of word `word` of `tile` that exist
+__device__ __forceinline__ uint32_t valid_mask(int64_t n, int64_t tile, int word) {
+    const int64_t rem = n - tile * kTileSamples - 32 * (int64_t)word;
+    return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+}
+
+__device__ __forceinline__ uint2* record(const PackArgs& a, int64_t tile, uint32_t key) {
+    return reinterpret_cast<uint2*>(a.planes) +
+           ((size_t)tile * (size_t)a.n_keys + (size_t)a.key_base + key) * kTileWords;
+}
+
+// -----------------------------------------------------------------------------------------
+// generic kernel: warp per (tile, variant); lane = sample within a word; ballot per word
+// -----------------------------------------------------------------------------------------
+struct LoadU8 {
+    // returns gt0 | gt1 << 8 | anc0 << 16 | anc1 << 24 of one sample
+    template <bool kAnc>
+    static __device__ __forceinline__ uint32_t load(const PackArgs& a, uint32_t col, int64_t s) {
+        const uint8_t* g = a.gt + s * a.gs + (int64_t)col * a.gv;
+        uint32_t x = (uint32_t)g[0] | ((uint32_t)g[a.gc] << 8);
+        if (kAnc) {
+            const uint8_t* l = a.anc + s * a.as + (int64_t)col * a.av;
+            x |= ((uint32_t)l[0] << 16) | ((uint32_t)l[a.ac] << 24);
+        }
+        return x;
+    }
+};
+
+struct LoadI32 {
+    // pgenlib allele codes (PgenReader.read_alleles_list): int32 matrix (rows, 2*n), element
+    // 2*s + c of row `col`; a.gv = row pitch in BYTES.  -9 (any value outside 0..253) =
+    // missing, stored by the reference as uint8 255 (haptools/data/genotypes.py:1388-1394).
+    template <bool kAnc>
+    static __device__ __forceinline__ uint32_t load(const PackArgs& a, uint32_t col, int64_t s) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(a.gt + (int64_t)col * a.gv) + s);
+        const uint32_t b0 = ((uint32_t)v.x > 253u) ? 255u : (uint32_t)v.x;
+        const uint32_t b1 = ((uint32_t)v.y > 253u) ? 255u : (uint32_t)v.y;
+        return b0 | (b1 << 8);
+    }
+};
+
+template <class Loader, bool kAnc>
+__global__ void __launch_bounds__(kPackThreads)
+pack_generic_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_vblocks;
+    const int64_t v = (int64_t)(blockIdx.x % n_vblocks) * kPackWarps + warp;
+    if (v >= a.n_vars) return;
+    const uint32_t col = __ldg(a.var_col + v);
+    const uint32_t kb = __ldg(a.var_key_off + v), ke = __ldg(a.var_key_off + v + 1);
+    const int64_t s0 = tile * kTileSamples + lane;
+
+    uint32_t x[32];
+    uint32_t fl = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+        const int64_t s = s0 + 32 * w;
+        x[w] = 0;
+        if (s < a.n) {
+            x[w] = Loader::template load<kAnc>(a, col, s);
+            fl |= qc_flags4(x[w] & 0xffffu);
+        }
+    }
+    publish_flags(a.flags, fl);
+
+    constexpr uint32_t m0 = kAnc ? 0x00ff00ffu : 0x000000ffu;
+    constexpr uint32_t m1 = kAnc ? 0xff00ff00u : 0x0000ff00u;
+    for (uint32_t k = kb; k < ke; ++k) {
+        uint32_t pat = (uint32_t)__ldg(a.key_allele + k) * 0x0101u;
+        if (kAnc) pat |= (uint32_t)__ldg(a.key_label + k) * 0x01010000u;
+        uint2 mine = make_uint2(0u, 0u);
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const bool valid = (s0 + 32 * w) < a.n;
+            const uint32_t d = x[w] ^ pat;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, valid && (d & m0) == 0);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, valid && (d & m1) == 0);
+            if (lane == w) mine = make_uint2(b0, b1);
+        }
+        record(a, tile, k)[lane] = mine;  // 256 B coalesced
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// variant-major kernel (s_strand == 1, s_samp == 2): warp per (tile, variant)
+// -----------------------------------------------------------------------------------------
+// 16 bytes = 8 samples x 2 strands of one variant; `nvalid` = how many of the 8 samples exist
+__device__ __forceinline__ uint4 load_chunk16(const uint8_t* p, int nvalid) {
+    if (nvalid >= 8) return __ldg(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int i = 0; i < 2 * nvalid; ++i) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool kAnc>
+__global__ void __launch_bounds__(kPackThreads)
+pack_vm_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_vblocks;
+    const int64_t v = (int64_t)(blockIdx.x % n_vblocks) * kPackWarps + warp;
+    if (v >= a.n_vars) return;
+    const uint32_t col = __ldg(a.var_col + v);
+    const uint32_t kb = __ldg(a.var_key_off + v), ke = __ldg(a.var_key_off + v + 1);
+    const int rows = (int)min((int64_t)kTileSamples, a.n - tile * kTileSamples);
+    const uint8_t* g = a.gt + (int64_t)col * a.gv + tile * (2 * kTileSamples);
+    const uint8_t* l = kAnc ? a.anc + (int64_t)col * a.av + tile * (2 * kTileSamples) : nullptr;
+
+    // y = strand-0 bytes, z = strand-1 bytes of the lane's 4 chunks (8 samples each)
+    uint32_t y[4][2], z[4][2], ay[4][2], az[4][2];
+    uint32_t fl = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = j * 32 + lane;
+        const int nvalid = rows - 8 * c;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (nvalid > 0) x = load_chunk16(g + 16 * c, nvalid);
+        if (a.flags) fl |= qc_flags4(x.x) | qc_flags4(x.y) | qc_flags4(x.z) | qc_flags4(x.w);
+        y[j][0] = prmt(x.x, x.y, 0x6420);
+        y[j][1] = prmt(x.z, x.w, 0x6420);
+        z[j][0] = prmt(x.x, x.y, 0x7531);
+        z[j][1] = prmt(x.z, x.w, 0x7531);
+        if (kAnc) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (nvalid > 0) q = load_chunk16(l + 16 * c, nvalid);
+            ay[j][0] = prmt(q.x, q.y, 0x6420);
+            ay[j][1] = prmt(q.z, q.w, 0x6420);
+            az[j][0] = prmt(q.x, q.y, 0x7531);
+            az[j][1] = prmt(q.z, q.w, 0x7531);
+        }
+    }
+    publish_flags(a.flags, fl);
+
+    for (uint32_t k = kb; k < ke; ++k) {
+        const uint32_t pat = (uint32_t)__ldg(a.key_allele + k) * 0x01010101u;
+        const uint32_t lpat = kAnc ? (uint32_t)__ldg(a.key_label + k) * 0x01010101u : 0u;
+        uint2* rec = record(a, tile, k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t f0a = eq_bytes_msb(y[j][0], pat), f0b = eq_bytes_msb(y[j][1], pat);
+            uint32_t f1a = eq_bytes_msb(z[j][0], pat), f1b = eq_bytes_msb(z[j][1], pat);
+            if (kAnc) {
+                f0a &= eq_bytes_msb(ay[j][0], lpat);
+                f0b &= eq_bytes_msb(ay[j][1], lpat);
+                f1a &= eq_bytes_msb(az[j][0], lpat);
+                f1b &= eq_bytes_msb(az[j][1], lpat);
+            }
+            const uint32_t m0 = nib(f0a) | (nib(f0b) << 4);  // 8 samples, strand 0
+            const uint32_t m1 = nib(f1a) | (nib(f1b) << 4);  // 8 samples, strand 1
+            // lanes 4m..4m+3 hold the 4 bytes of word 8*j + m: merge them
+            uint32_t t = (m0 | (m1 << 16)) << (8 * (lane & 1));
+            t |= __shfl_xor_sync(0xffffffffu, t, 1);
+            const uint32_t u = __shfl_xor_sync(0xffffffffu, t, 2);
+            const uint32_t lo = (lane & 2) ? u : t, hi = (lane & 2) ? t : u;
+            if ((lane & 3) == 0) {
+                const int word = 8 * j + (lane >> 2);
+                const uint32_t vm = valid_mask(a.n, tile, word);
+                rec[word] = make_uint2(prmt(lo, hi, 0x5410) & vm, prmt(lo, hi, 0x7632) & vm);
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// sample-major kernel (s_strand == 1, s_var == 2): CTA per (tile, 128 columns); lane = 4
+// columns (8 bytes of every sample row), warp = 4 words (128 samples)
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 load_cols8(const uint8_t* p, int ncols) {
+    if (ncols >= 4) return __ldg(reinterpret_cast<const uint2*>(p));
+    uint32_t w[2] = {0u, 0u};
+    for (int i = 0; i < 2 * ncols; ++i) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
+    return make_uint2(w[0], w[1]);
+}
+
+template <bool kAnc>
+__global__ void __launch_bounds__(kPackThreads)
+pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_cblocks;
+    const int64_t col0 = (cblock0 + blockIdx.x % n_cblocks) * kSmCols + 4 * lane;
+    const int ncols = (int)min((int64_t)4, a.n_cols - col0);  // may be <= 0
+    if (ncols <= 0) return;
+
+    // which of my 4 columns are referenced, and their key ranges
+    uint32_t kb[4], nk[4];
+    uint32_t rounds = 0, refmask[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        kb[i] = 0;
+        nk[i] = 0;
+        if (i < ncols) {
+            const int32_t v = __ldg(a.col_var + col0 + i);
+            if (v >= 0) {
+                kb[i] = __ldg(a.var_key_off + v);
+                nk[i] = __ldg(a.var_key_off + v + 1) - kb[i];
+                refmask[i >> 1] |= 0xffffu << (16 * (i & 1));
+            }
+        }
+        rounds = max(rounds, nk[i]);
+    }
+    if (rounds == 0) return;
+
+    const uint8_t* g = a.gt + col0 * 2;
+    const uint8_t* l = kAnc ? a.anc + col0 * 2 : nullptr;
+    const int64_t s_warp = tile * kTileSamples + 128 * warp;
+    uint32_t fl = 0;
+
+    for (uint32_t r = 0; r < rounds; ++r) {
+        // per-byte patterns of this round's key of each column
+        uint32_t pb[4] = {0u, 0u, 0u, 0u}, lb[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r < nk[i]) {
+                pb[i] = __ldg(a.key_allele + kb[i] + r);
+                if (kAnc) lb[i] = __ldg(a.key_label + kb[i] + r);
+            }
+        }
+        const uint2 pat = make_uint2((pb[0] | (pb[1] << 16)) * 0x0101u, (pb[2] | (pb[3] << 16)) * 0x0101u);
+        const uint2 lpat = make_uint2((lb[0] | (lb[1] << 16)) * 0x0101u, (lb[2] | (lb[3] << 16)) * 0x0101u);
+
+        // res[w4][2*i + c]: word (4*warp + w4) of column i, strand c
+        uint32_t res[4][8];
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+            uint2 G[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t s_first = s_warp + 32 * w4 + 8 * q;
+                uint2 x[8], c[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int64_t s = s_first + rr;
+                    x[rr] = make_uint2(0u, 0u);
+                    if (s < a.n) x[rr] = load_cols8(g + s * a.gs, ncols);
+                    if (kAnc) {
+                        c[rr] = make_uint2(0u, 0u);
+                        if (s < a.n) c[rr] = load_cols8(l + s * a.as, ncols);
+                    }
+                }
+                uint2 acc = make_uint2(0u, 0u);
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    uint2 f = make_uint2(eq_bytes_msb(x[rr].x, pat.x), eq_bytes_msb(x[rr].y, pat.y));
+                    if (kAnc) {
+                        f.x &= eq_bytes_msb(c[rr].x, lpat.x);
+                        f.y &= eq_bytes_msb(c[rr].y, lpat.y);
+                    }
+                    // row rr enters at bit 7 of its byte and ends at bit rr after 7 - rr shifts
+                    acc.x = (acc.x >> 1) | f.x;
+                    acc.y = (acc.y >> 1) | f.y;
+                    if (r == 0 && a.flags)
+                        fl |= qc_flags4(x[rr].x & refmask[0]) | qc_flags4(x[rr].y & refmask[1]);
+                }
+                G[q] = acc;
+            }
+            // 4x4 byte transposes: byte b of G[q] (8 samples of byte-column b) -> word per column
+            const uint32_t vm = valid_mask(a.n, tile, 4 * warp + w4);
+            {
+                const uint32_t t0 = prmt(G[0].x, G[1].x, 0x5140), t1 = prmt(G[2].x, G[3].x, 0x5140);
+                const uint32_t t2 = prmt(G[0].x, G[1].x, 0x7362), t3 = prmt(G[2].x, G[3].x, 0x7362);
+                res[w4][0] = prmt(t0, t1, 0x5410) & vm;
+                res[w4][1] = prmt(t0, t1, 0x7632) & vm;
+                res[w4][2] = prmt(t2, t3, 0x5410) & vm;
+                res[w4][3] = prmt(t2, t3, 0x7632) & vm;
+            }
+            {
+                const uint32_t t0 = prmt(G[0].y, G[1].y, 0x5140), t1 = prmt(G[2].y, G[3].y, 0x5140);
+                const uint32_t t2 = prmt(G[0].y, G[1].y, 0x7362), t3 = prmt(G[2].y, G[3].y, 0x7362);
+                res[w4][4] = prmt(t0, t1, 0x5410) & vm;
+                res[w4][5] = prmt(t0, t1, 0x7632) & vm;
+                res[w4][6] = prmt(t2, t3, 0x5410) & vm;
+                res[w4][7] = prmt(t2, t3, 0x7632) & vm;
+            }
+        }
+        // one full 32-byte sector per (key, warp): words 4*warp .. 4*warp+3, both strands
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r < nk[i]) {
+                uint4* dst = reinterpret_cast<uint4*>(record(a, tile, kb[i] + r) + 4 * warp);
+                dst[0] = make_uint4(res[0][2 * i], res[0][2 * i + 1], res[1][2 * i], res[1][2 * i + 1]);
+                dst[1] = make_uint4(res[2][2 * i], res[2][2 * i + 1], res[3][2 * i], res[3][2 * i + 1]);
+            }
+        }
+    }
+    publish_flags(a.flags, fl);
+}
+
+static bool aligned(const void* p, int64_t stride, int to) {
+    return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)stride) & (uintptr_t)(to - 1)) == 0;
+}
+
+// Launches `kernel` over all tiles; blockIdx.x = tile-major (tile, x-block).  The kernels take
+// (PackArgs, uint32 n_xblocks, [int64 extra,] int64 tile0).
+template <class K>
+static int launch_tiled(K kernel, const PackArgs& a, int64_t n_xblocks, int64_t extra,
+                        bool has_extra, cudaStream_t st) {
+    const int64_t n_tiles = ht_num_tiles(a.n);
+    if (n_xblocks <= 0 || n_tiles <= 0) return HT_OK;
+    if (n_xblocks > 0x7fffffff) {
+        set_error("pack: too many variant blocks (%lld)", (long long)n_xblocks);
+        return HT_ERR_UNSUPPORTED;
+    }
+    uint32_t nxb = (uint32_t)n_xblocks;
+    // a grid holds at most 2^31-1 blocks: launch ranges of tiles
+    const int64_t tiles_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_xblocks);
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
+        const int64_t nt = min(tiles_per_launch, n_tiles - t0);
+        void* args_extra[] = {(void*)&a, (void*)&nxb, (void*)&extra, (void*)&t0};
+        void* args_plain[] = {(void*)&a, (void*)&nxb, (void*)&t0};
+        HT_CUDA_TRY(cudaLaunchKernel((const void*)kernel, dim3((unsigned)(nt * n_xblocks)),
+                                     dim3(kPackThreads), has_extra ? args_extra : args_plain, 0, st));
+    }
+    return HT_OK;
+}
+
+static int check_pack(const PackArgs& a) {
+    if (a.n < 0 || a.n_vars < 0 || a.n_keys < 0 || a.key_base < 0) return bad_arg("negative size");
+    if (a.n_vars == 0 || a.n == 0) return HT_OK;
+    if (!a.gt) return bad_arg("gt is NULL");
+    if (!a.var_col || !a.var_key_off || !a.key_allele) return bad_arg("variant/key tables are NULL");
+    if (!a.planes) return bad_arg("planes is NULL");
+    if (reinterpret_cast<uintptr_t>(a.planes) & 15) return bad_arg("planes must be 16-byte aligned");
+    if ((a.anc != nullptr) != (a.key_label != nullptr))
+        return bad_arg("anc and key_label must be given together");
+    return HT_OK;
+}
+
+}  // namespace ht
+
+extern "C" {
+
+int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t gt_s_strand,
+               const uint8_t* anc, int64_t anc_s_samp, int64_t anc_s_var, int64_t anc_s_strand,
+               int64_t n_samples, const uint32_t* var_col, const uint32_t* var_key_off,
+               const uint8_t* key_allele, const uint8_t* key_label, int64_t n_vars,
+               int64_t n_keys, const int32_t* col_var, int64_t n_cols, uint32_t* planes,
+               uint32_t* flags, int mode, void* stream) {
+    using namespace ht;
+    PackArgs a;
+    a.gt = gt; a.gs = gt_s_samp; a.gv = gt_s_var; a.gc = gt_s_strand;
+    a.anc = anc; a.as = anc_s_samp; a.av = anc_s_var; a.ac = anc_s_strand;
+    a.n = n_samples;
+    a.var_col = var_col; a.var_key_off = var_key_off;
+    a.key_allele = key_allele; a.key_label = key_label;
+    a.col_var = col_var; a.n_cols = n_cols;
+    a.n_vars = n_vars; a.n_keys = n_keys; a.key_base = 0;
+    a.planes = planes; a.flags = flags;
+    if (int rc = check_pack(a)) return rc;
+    if (n_vars == 0 || n_samples == 0) return HT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const bool vm_ok = gt_s_strand == 1 && gt_s_samp == 2 && aligned(gt, gt_s_var, 16) &&
+                       (!anc || (anc_s_strand == 1 && anc_s_samp == 2 && aligned(anc, anc_s_var, 16)));
+    const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 8) && col_var &&
+                       n_cols > 0 &&
+                       (!anc || (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 8)));
+    if (mode == HT_PACK_AUTO)
+        mode = vm_ok ? HT_PACK_VARIANT_MAJOR : (sm_ok ? HT_PACK_SAMPLE_MAJOR : HT_PACK_GENERIC);
+
+    const int64_t n_vblocks = (n_vars + kPackWarps - 1) / kPackWarps;
+    switch (mode) {
+        case HT_PACK_GENERIC:
+            return anc ? launch_tiled(pack_generic_kernel<LoadU8, true>, a, n_vblocks, 0, false, st)
+                       : launch_tiled(pack_generic_kernel<LoadU8, false>, a, n_vblocks, 0, false, st);
+        case HT_PACK_VARIANT_MAJOR:
+            if (!vm_ok) {
+                set_error("variant-major pack needs s_strand=1, s_samp=2 and 16-byte aligned rows");
+                return HT_ERR_UNSUPPORTED;
+            }
+            return anc ? launch_tiled(pack_vm_kernel<true>, a, n_vblocks, 0, false, st)
+                       : launch_tiled(pack_vm_kernel<false>, a, n_vblocks, 0, false, st);
+        case HT_PACK_SAMPLE_MAJOR: {
+            if (!sm_ok) {
+                set_error("sample-major pack needs s_strand=1, s_var=2, 8-byte aligned rows and col_var");
+                return HT_ERR_UNSUPPORTED;
+            }
+            const int64_t n_cblocks = (n_cols + kSmCols - 1) / kSmCols;
+            return anc ? launch_tiled(pack_sm_kernel<true>, a, n_cblocks, 0, true, st)
+                       : launch_tiled(pack_sm_kernel<false>, a, n_cblocks, 0, true, st);
+        }
+        default:
+            return bad_arg("unknown pack mode");
+    }
+}
+
+int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_samples,
+                const uint32_t* var_col, const uint32_t* var_key_off, const uint8_t* key_allele,
+                int64_t n_vars, int64_t key_base, int64_t n_keys_total, uint32_t* planes,
+                uint32_t* flags, void* stream) {
+    using namespace ht;
+    PackArgs a;
+    a.gt = reinterpret_cast<const uint8_t*>(alleles);
+    a.gs = 8; a.gv = row_pitch_elems * 4; a.gc = 4;
+    a.anc = nullptr; a.as = a.av = a.ac = 0;
+    a.n = n_samples;
+    a.var_col = var_col; a.var_key_off = var_key_off;
+    a.key_allele = key_allele; a.key_label = nullptr;
+    a.col_var = nullptr; a.n_cols = 0;
+    a.n_vars = n_vars; a.n_keys = n_keys_total; a.key_base = key_base;
+    a.planes = planes; a.flags = flags;
+    if (int rc = check_pack(a)) return rc;
+    if (n_vars == 0 || n_samples == 0) return HT_OK;
+    if (row_pitch_elems < 2 * n_samples) return bad_arg("row_pitch_elems < 2 * n_samples");
+    if (!aligned(alleles, a.gv, 8)) return bad_arg("int32 allele rows must be 8-byte aligned");
+    const int64_t n_vblocks = (n_vars + kPackWarps - 1) / kPackWarps;
+    return launch_tiled(pack_generic_kernel<LoadI32, false>, a, n_vblocks, 0, false,
+                        (cudaStream_t)stream);
+}
+
+}  // extern "C"

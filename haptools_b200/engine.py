@@ -1,0 +1,337 @@
+"""
+Device execution of the haplotype transform through the C-ABI (include/haptools_cuda.h).
+
+torch is plumbing only: device memory, streams and events.  All arithmetic happens in the
+hand-written kernels of libhaptools_cuda.so; there is no CPU fallback -- without a CUDA
+device (or without the built library) every entry point raises.
+
+Two entry points:
+  transform_device  genotypes already resident in HBM (a CUDA torch tensor with arbitrary
+                    strides) -> result tensor on the device
+  transform_host    genotypes in a host numpy array (any of the reference's layouts,
+                    SURVEY.md 4c) -> numpy bool array; sample chunks are streamed with
+                    double-buffered H2D / compute / D2H on three streams, the analogue of
+                    the reference's variant-chunked PGEN reads
+                    (haptools/data/genotypes.py:1353-1406)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cuda
+from ._cuda import HaptoolsCudaError, check
+from .plan import TransformPlan
+
+TILE = _cuda.TILE_SAMPLES
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise HaptoolsCudaError(
+            "haptools_b200 needs a CUDA device (B200, sm_100a): the transform has no CPU fallback"
+        )
+    _cuda.lib()
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream_ptr(stream=None) -> int:
+    return (stream or torch.cuda.current_stream()).cuda_stream
+
+
+class DevicePlan:
+    """A TransformPlan uploaded to one device (a few MB; replicated on every rank)."""
+
+    def __init__(self, plan: TransformPlan, device=None):
+        require_cuda()
+        self.plan = plan
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+        def up(a, dtype):
+            # uint32 tables are carried as int32 tensors (same bits)
+            return None if a is None else torch.from_numpy(np.ascontiguousarray(a).view(dtype)).to(self.device)
+
+        self.var_col = up(plan.var_col, np.int32)
+        self.var_key_off = up(plan.var_key_off, np.int32)
+        self.key_allele = up(plan.key_allele, np.uint8)
+        self.key_label = up(plan.key_label, np.uint8)
+        self.hap_off = up(plan.hap_off, np.int32)
+        self.hap_key = up(plan.hap_key, np.int32)
+        self.col_var = up(plan.col_var(), np.int32)
+
+    n_haps = property(lambda self: self.plan.n_haps)
+    n_keys = property(lambda self: self.plan.n_keys)
+    n_vars = property(lambda self: self.plan.n_vars)
+
+
+def plane_bytes(n_samples: int, n_keys: int) -> int:
+    return int(_cuda.lib().ht_plane_bytes(n_samples, n_keys))
+
+
+def alloc_planes(n_samples: int, n_keys: int, device) -> torch.Tensor:
+    return torch.empty(max(plane_bytes(n_samples, n_keys), 16) // 4, dtype=torch.int32, device=device)
+
+
+def out_pitch(n_haps: int) -> int:
+    """Row pitch (bytes) of a device result buffer: 16-byte aligned rows keep the transform
+    kernel on its 128-bit store path for any number of haplotypes."""
+    return max(16, (2 * n_haps + 15) // 16 * 16)
+
+
+def pack(dplan: DevicePlan, gt_ptr: int, gt_strides, n_samples: int, planes: torch.Tensor,
+         anc_ptr: int = 0, anc_strides=(0, 0, 0), flags: torch.Tensor = None,
+         mode: int = _cuda.HT_PACK_AUTO, stream=None) -> None:
+    """K1 on raw device pointers; strides are (sample, variant, strand) in bytes."""
+    if dplan.plan.has_ancestry != bool(anc_ptr):
+        raise ValueError("ancestry plan and ancestry array must be given together")
+    check(
+        _cuda.lib().ht_pack_u8(
+            gt_ptr, *map(int, gt_strides), anc_ptr, *map(int, anc_strides), n_samples,
+            _ptr(dplan.var_col), _ptr(dplan.var_key_off), _ptr(dplan.key_allele), _ptr(dplan.key_label),
+            dplan.n_vars, dplan.n_keys, _ptr(dplan.col_var), dplan.plan.n_cols,
+            _ptr(planes), _ptr(flags), mode, _stream_ptr(stream),
+        ),
+        "ht_pack_u8",
+    )
+
+
+def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_ptr: int, pitch: int,
+                 stream=None) -> None:
+    """K2 on raw device pointers."""
+    check(
+        _cuda.lib().ht_transform_u8(
+            _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
+            dplan.n_haps, out_ptr, pitch, _stream_ptr(stream),
+        ),
+        "ht_transform_u8",
+    )
+
+
+def transform_bits(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_bits: torch.Tensor,
+                   stream=None) -> None:
+    check(
+        _cuda.lib().ht_transform_bits(
+            _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
+            dplan.n_haps, _ptr(out_bits), _stream_ptr(stream),
+        ),
+        "ht_transform_bits",
+    )
+
+
+def count_bits(bits: torch.Tensor, n_samples: int, n_haps: int, stream=None) -> torch.Tensor:
+    """Per-haplotype allele counts of a bit-packed result (numerator of check_maf,
+    haptools/data/genotypes.py:559-625)."""
+    counts = torch.empty(n_haps, dtype=torch.int64, device=bits.device)
+    check(_cuda.lib().ht_count_bits(_ptr(bits), n_samples, n_haps, _ptr(counts), _stream_ptr(stream)), "ht_count_bits")
+    return counts
+
+
+def _check_gt_tensor(gt: torch.Tensor, what: str) -> None:
+    if not isinstance(gt, torch.Tensor) or not gt.is_cuda:
+        raise TypeError(f"{what} must be a CUDA tensor")
+    if gt.dtype not in (torch.uint8, torch.bool) or gt.dim() != 3 or gt.shape[2] < 2:
+        raise ValueError(f"{what} must have shape (samples, variants, >=2) and dtype uint8 or bool")
+
+
+def transform_device(gt: torch.Tensor, dplan: DevicePlan, ancestry: torch.Tensor = None,
+                     out: torch.Tensor = None, planes: torch.Tensor = None, fmt: str = "u8",
+                     flags: torch.Tensor = None, pack_mode: int = _cuda.HT_PACK_AUTO):
+    """
+    Transform genotypes resident on the device.
+
+    gt        (n, p, >=2) uint8/bool CUDA tensor, any strides (never copied)
+    ancestry  (n, p, 2) uint8 CUDA tensor for ancestry plans
+    fmt       "u8": returns an (n, H, 2) uint8 tensor (0/1 bytes == numpy bool bytes);
+              "bits": returns the bit-packed result (tiles, H, 32, 2) int32
+    """
+    require_cuda()
+    _check_gt_tensor(gt, "gt")
+    n, p = int(gt.shape[0]), int(gt.shape[1])
+    if p != dplan.plan.n_cols:
+        raise ValueError(f"plan was made for {dplan.plan.n_cols} variant columns, genotypes have {p}")
+    if ancestry is not None:
+        _check_gt_tensor(ancestry, "ancestry")
+        if tuple(ancestry.shape[:2]) != (n, p):
+            raise ValueError("ancestry and genotypes differ in shape")
+    H = dplan.n_haps
+    with torch.cuda.device(gt.device):
+        if planes is None:
+            planes = alloc_planes(n, dplan.n_keys, gt.device)
+        pack(dplan, gt.data_ptr(), gt.stride(), n, planes,
+             _ptr(ancestry), ancestry.stride() if ancestry is not None else (0, 0, 0), flags, pack_mode)
+        if fmt == "bits":
+            tiles = (n + TILE - 1) // TILE
+            if out is None:
+                out = torch.empty((tiles, H, 32, 2), dtype=torch.int32, device=gt.device)
+            transform_bits(dplan, planes, n, out)
+            return out
+        if fmt != "u8":
+            raise ValueError("fmt must be 'u8' or 'bits'")
+        if out is None:
+            pitch = out_pitch(H)
+            buf = torch.empty((n, pitch), dtype=torch.uint8, device=gt.device)
+            out = buf[:, : 2 * H].view(n, H, 2) if pitch == 2 * H else buf[:, : 2 * H].unflatten(1, (H, 2))
+        else:
+            if out.dtype != torch.uint8 or tuple(out.shape) != (n, H, 2) or (H and out.stride()[1:] != (2, 1)):
+                raise ValueError("out must be a uint8 tensor of shape (n, H, 2) with contiguous rows")
+        transform_u8(dplan, planes, n, out.data_ptr(), int(out.stride(0)) if n else 2 * H)
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# host arrays
+# --------------------------------------------------------------------------------------
+class _Region:
+    """The bytes of a[s0:s1, :, :2] as a pitched 2-D region of host memory."""
+
+    __slots__ = ("ptr", "rows", "width", "pitch", "sample_major", "ss", "sv", "sc", "keep")
+
+    def dev_pitch(self) -> int:
+        return max(16, (self.width + 15) // 16 * 16)
+
+    def dev_strides(self):
+        dp = self.dev_pitch()
+        return (dp, self.sv, self.sc) if self.sample_major else (self.ss, dp, self.sc)
+
+    def dev_bytes(self) -> int:
+        return self.rows * self.dev_pitch()
+
+
+def _region(a: np.ndarray, s0: int, s1: int) -> _Region:
+    n, p = s1 - s0, a.shape[1]
+    ss, sv, sc = a.strides
+    r = _Region()
+    r.keep = None
+    ok = ss > 0 and sv > 0 and sc > 0
+    if ok and ss >= sv:
+        width = (p - 1) * sv + sc + 1
+        ok = width <= ss or n <= 1
+        sample_major = True
+    elif ok:
+        width = (n - 1) * ss + sc + 1
+        ok = width <= sv or p <= 1
+        sample_major = False
+    if not ok:
+        # exotic views (negative or overlapping strides): one contiguous host copy
+        c = np.ascontiguousarray(a[s0:s1, :, :2])
+        r.keep = c
+        a, s0 = c, 0
+        ss, sv, sc = c.strides
+        width, sample_major = (p - 1) * sv + sc + 1, True
+    r.ptr = a.ctypes.data + s0 * ss
+    r.sample_major = sample_major
+    r.ss, r.sv, r.sc = ss, sv, sc
+    r.width = width
+    r.rows, r.pitch = (n, ss) if sample_major else (p, sv)
+    return r
+
+
+def _copy2d(dst: int, dpitch: int, src: int, spitch: int, width: int, rows: int, kind: int, stream) -> None:
+    check(_cuda.lib().ht_copy2d(dst, dpitch, src, spitch, width, rows, kind, stream.cuda_stream), "ht_copy2d")
+
+
+def default_chunk(n: int, p: int, n_haps: int, target_bytes: int = 512 << 20) -> int:
+    per_sample = max(2 * n_haps, 3 * p, 1)
+    rows = max(TILE, target_bytes // per_sample // TILE * TILE)
+    return int(min(max(n, 1), rows))
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """A page-locked numpy array (owned by a torch pinned tensor kept alive through .base)."""
+    require_cuda()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+    return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
+def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,
+                   chunk_samples: int = None, out: np.ndarray = None, pin_output: bool = None,
+                   dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO) -> np.ndarray:
+    """
+    gt (n, p, 2|3) uint8/bool host array (a view is fine: VCF-style transposed, PGEN-style
+    with a phase column, C-contiguous ...) -> (n, H, 2) numpy bool, bit-identical to the
+    reference's ``hap_gts.data``.
+    """
+    require_cuda()
+    if gt.ndim != 3 or gt.shape[2] < 2 or gt.dtype not in (np.uint8, np.bool_):
+        raise ValueError("genotypes must have shape (samples, variants, >=2) and dtype uint8 or bool")
+    n, p = gt.shape[0], gt.shape[1]
+    if p != plan.n_cols:
+        raise ValueError(f"plan was made for {plan.n_cols} variant columns, genotypes have {p}")
+    if plan.has_ancestry:
+        if ancestry is None or ancestry.shape[:2] != gt.shape[:2] or ancestry.shape[2] < 2 or ancestry.dtype != np.uint8:
+            raise ValueError("ancestry must be a uint8 array shaped like the genotypes")
+    H = plan.n_haps
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if out is None:
+        nbytes = n * H * 2
+        if pin_output is None:
+            pin_output = 0 < nbytes <= (4 << 30)
+        out = pinned_empty((n, H, 2)) if pin_output else np.empty((n, H, 2), dtype=np.uint8)
+    elif out.shape != (n, H, 2) or out.dtype.itemsize != 1 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous 1-byte array of shape (n, H, 2)")
+    result = out.view(np.bool_)
+    if n == 0 or H == 0:
+        return result
+    with torch.cuda.device(dev):
+        if dplan is None:
+            dplan = DevicePlan(plan, dev)
+        chunk = chunk_samples or default_chunk(n, p, H)
+        chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
+        bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+        nbuf = min(2, len(bounds))
+        pitch = out_pitch(H)
+        regs = [_region(gt, *bounds[0])]
+        gt_bytes = max(_region(gt, *b).dev_bytes() for b in bounds[:1] + bounds[-1:])
+        gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        anc_buf = [None] * nbuf
+        if plan.has_ancestry:
+            anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in bounds[:1] + bounds[-1:])
+            anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        out_buf = [torch.empty(chunk * pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        planes = alloc_planes(chunk, plan.n_keys, dev)
+        s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        for s in (s_in, s_cmp, s_out):
+            s.wait_stream(cur)
+        ev_h2d = [None] * nbuf
+        ev_cmp = [None] * nbuf
+        ev_d2h = [None] * nbuf
+        keep = []
+        del regs
+        out_ptr = out.ctypes.data
+        for k, (s0, s1) in enumerate(bounds):
+            b = k % nbuf
+            rows = s1 - s0
+            # H2D (the previous user of this input buffer must have been packed)
+            if ev_cmp[b] is not None:
+                s_in.wait_event(ev_cmp[b])
+            rg = _region(gt, s0, s1)
+            keep.append(rg.keep)
+            _copy2d(gt_buf[b].data_ptr(), rg.dev_pitch(), rg.ptr, rg.pitch, rg.width, rg.rows, _cuda.HT_COPY_H2D, s_in)
+            ra = None
+            if plan.has_ancestry:
+                ra = _region(ancestry, s0, s1)
+                keep.append(ra.keep)
+                _copy2d(anc_buf[b].data_ptr(), ra.dev_pitch(), ra.ptr, ra.pitch, ra.width, ra.rows, _cuda.HT_COPY_H2D, s_in)
+            ev_h2d[b] = s_in.record_event()
+            # compute (the previous result in this output buffer must have left)
+            s_cmp.wait_event(ev_h2d[b])
+            if ev_d2h[b] is not None:
+                s_cmp.wait_event(ev_d2h[b])
+            pack(dplan, gt_buf[b].data_ptr(), rg.dev_strides(), rows, planes,
+                 _ptr(anc_buf[b]) if ra else 0, ra.dev_strides() if ra else (0, 0, 0), None, pack_mode, s_cmp)
+            transform_u8(dplan, planes, rows, out_buf[b].data_ptr(), pitch, s_cmp)
+            ev_cmp[b] = s_cmp.record_event()
+            # D2H
+            s_out.wait_event(ev_cmp[b])
+            _copy2d(out_ptr + s0 * 2 * H, 2 * H, out_buf[b].data_ptr(), pitch, 2 * H, rows, _cuda.HT_COPY_D2H, s_out)
+            ev_d2h[b] = s_out.record_event()
+        s_out.synchronize()
+        s_cmp.synchronize()
+        s_in.synchronize()
+        cur.wait_stream(s_out)
+    return result

@@ -1,0 +1,197 @@
+"""
+Host planner of the haplotype transform: turns haplotype objects (or flat arrays) into the
+small index tables the CUDA kernels consume (include/haptools_cuda.h).
+
+It mirrors, step by step, what the reference does on the host before its numpy arithmetic
+(haptools/data/haplotypes.py:1363-1401, haptools/transform.py:96-135) -- including the
+exceptions it raises -- but resolves ``key -> column of gts.data`` instead of copying the
+columns (``gts.subset``, haptools/data/genotypes.py:440).
+
+Vocabulary
+  key    one distinct (variant column, allele index[, ancestry label]) a haplotype asks for;
+         the reference's ``alleles`` dict entry, with the haplotype's ancestry label folded
+         in for the ancestry-aware classes
+  CSR    ``hap_key[hap_off[h]:hap_off[h+1]]`` = keys of haplotype ``h`` (the reference's
+         ``idxs[h]``)
+Keys are numbered by (column, allele, label) so that the keys of one variant are consecutive
+(``var_key_off``): the pack kernel then reads every genotype column once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+_U32_MAX = 0xFFFFFFFF
+
+
+@dataclass
+class TransformPlan:
+    """Index tables for one (haplotype set, genotype column layout) pair; all numpy."""
+
+    n_cols: int  # number of variant columns of the genotype array the plan refers to
+    var_col: np.ndarray  # (V,) uint32, ascending: referenced columns
+    var_key_off: np.ndarray  # (V+1,) uint32
+    key_allele: np.ndarray  # (A,) uint8
+    key_label: np.ndarray | None  # (A,) uint8, ancestry plans only
+    hap_off: np.ndarray  # (H+1,) uint32
+    hap_key: np.ndarray  # (K,) uint32
+
+    @property
+    def n_haps(self) -> int:
+        return len(self.hap_off) - 1
+
+    @property
+    def n_vars(self) -> int:
+        return len(self.var_col)
+
+    @property
+    def n_keys(self) -> int:
+        return len(self.key_allele)
+
+    @property
+    def n_refs(self) -> int:
+        return len(self.hap_key)
+
+    @property
+    def has_ancestry(self) -> bool:
+        return self.key_label is not None
+
+    def col_var(self) -> np.ndarray:
+        """Dense inverse of ``var_col``: (n_cols,) int32, -1 for unreferenced columns."""
+        out = np.full(self.n_cols, -1, dtype=np.int32)
+        out[self.var_col] = np.arange(self.n_vars, dtype=np.int32)
+        return out
+
+    def key_col(self) -> np.ndarray:
+        """Column of each key, (A,) uint32."""
+        return np.repeat(self.var_col, np.diff(self.var_key_off.astype(np.int64)))
+
+    def algorithmic_bytes(self, n_samples: int) -> dict:
+        """compulsory bytes of the pack and transform kernels."""
+        words = (n_samples + 31) // 32
+        plane = self.n_keys * 2 * words * 4
+        gt = n_samples * self.n_vars * 2
+        out = n_samples * self.n_haps * 2
+        pack = gt * (2 if self.has_ancestry else 1) + plane
+        return {"pack": pack, "transform": plane + out, "total": pack + plane + out, "planes": plane, "gt": gt, "out": out}
+
+
+def plan_from_refs(
+    ref_col: np.ndarray,
+    ref_allele: np.ndarray,
+    hap_off: np.ndarray,
+    n_cols: int,
+    ref_label: np.ndarray | None = None,
+) -> TransformPlan:
+    """
+    Build a plan from one (column, allele[, label]) triple per haplotype-variant reference:
+    reference ``j`` belongs to the haplotype ``h`` with ``hap_off[h] <= j < hap_off[h+1]``.
+    De-duplicates the triples into keys (haptools/data/haplotypes.py:1382-1386).
+    """
+    ref_col = np.asarray(ref_col, dtype=np.int64)
+    ref_allele = np.asarray(ref_allele, dtype=np.int64)
+    hap_off = np.asarray(hap_off, dtype=np.int64)
+    n_refs = len(ref_col)
+    if len(hap_off) == 0 or hap_off[0] != 0 or hap_off[-1] != n_refs or np.any(np.diff(hap_off) < 0):
+        raise ValueError("hap_off is not a valid CSR offset array")
+    if n_refs > _U32_MAX or n_cols > _U32_MAX:
+        raise ValueError("too many haplotype alleles / variants for 32-bit indices")
+    if n_refs and (ref_col.min() < 0 or ref_col.max() >= n_cols):
+        raise ValueError("a haplotype references a variant column outside the genotypes")
+    if n_refs and (ref_allele.min() < 0 or ref_allele.max() > 255):
+        raise ValueError("allele indices must fit in a uint8")
+    packed = (ref_col << 16) | (ref_allele << 8)
+    if ref_label is not None:
+        ref_label = np.asarray(ref_label, dtype=np.int64)
+        if n_refs and (ref_label.min() < 0 or ref_label.max() > 255):
+            raise ValueError("ancestry labels must fit in a uint8")
+        packed = packed | ref_label
+    keys, inverse = np.unique(packed, return_inverse=True)
+    key_col = (keys >> 16).astype(np.uint32)
+    var_col, first = np.unique(key_col, return_index=True)
+    var_key_off = np.concatenate([first, [len(keys)]]).astype(np.uint32)
+    return TransformPlan(
+        n_cols=int(n_cols),
+        var_col=var_col.astype(np.uint32),
+        var_key_off=var_key_off,
+        key_allele=((keys >> 8) & 0xFF).astype(np.uint8),
+        key_label=(keys & 0xFF).astype(np.uint8) if ref_label is not None else None,
+        hap_off=hap_off.astype(np.uint32),
+        hap_key=inverse.reshape(-1).astype(np.uint32),
+    )
+
+
+def _variant_columns(gts, var_ids: Sequence[str], who: str) -> list:
+    """``id -> column`` through ``Genotypes.index`` (duplicate IDs raise there,
+    haptools/data/genotypes.py:372-379); absent IDs raise instead of the reference's
+    misaligned gather."""
+    gts.index(samples=False, variants=True)
+    var_idx = gts._var_idx
+    missing = [v for v in var_ids if v not in var_idx]
+    if missing:
+        raise ValueError(
+            f"Variants {set(missing)} are present in {who} but absent in the provided genotypes"
+        )
+    return [var_idx[v] for v in var_ids]
+
+
+def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str = None,
+                         unknown_label: str = "raise"):
+    """
+    ``haps``: Haplotype objects (``.variants`` of objects with ``.id``/``.allele``; with
+    ``ancestry=True`` also ``.ancestry``); ``gts``: a GenotypesVCF-like object with
+    ``.data``, a structured ``.variants`` (``id``, ``alleles``) and, with ``ancestry=True``,
+    ``.ancestry_labels``.
+
+    Follows haptools/data/haplotypes.py:1375-1401 (plain) and haptools/transform.py:103-135
+    (ancestry).  ``unknown_label="raise"`` is the plural form's behaviour for a population
+    that is not in ``ancestry_labels`` (OverflowError from ``uint8 <- -1`` on numpy >= 2,
+    haptools/transform.py:115); ``"never"`` is the single-haplotype form's (-1 never equals a
+    label, haptools/transform.py:62-67): returns ``(plan, never)`` with ``never[h]`` True for
+    haplotypes that cannot be present.
+    """
+    # (variant ID, allele) -> index, in first-seen order, as the reference builds it
+    alleles: dict = {}
+    idxs = [None] * len(haps)
+    ancestries = np.empty(len(haps), dtype=np.uint8) if ancestry else None
+    never = np.zeros(len(haps), dtype=np.bool_)
+    count = 0
+    for i, hap in enumerate(haps):
+        if ancestry:
+            label = gts.ancestry_labels.get(hap.ancestry, -1)
+            if label == -1 and unknown_label == "never":
+                never[i] = len(hap.variants) > 0
+                label = 0
+            # uint8 <- -1 raises OverflowError on numpy >= 2, exactly like transform.py:115
+            ancestries[i] = label
+        idxs[i] = np.empty(len(hap.variants), dtype=np.uintc)
+        for j, variant in enumerate(hap.variants):
+            key = (variant.id, variant.allele)
+            if key not in alleles:
+                alleles[key] = count
+                count += 1
+            idxs[i][j] = alleles[key]
+    cols = _variant_columns(gts, [k[0] for k in alleles], who or "the haplotypes")
+    var_alleles = gts.variants["alleles"] if len(alleles) else ()
+    as_bool = gts.data.dtype == np.bool_
+    if ancestry:
+        # biallelic semantics: any non-REF string is 1 (haptools/transform.py:128-134)
+        allele_arr = [int(allele != var_alleles[c][0]) for c, (_, allele) in zip(cols, alleles)]
+    else:
+        try:
+            allele_arr = [var_alleles[c].index(allele) for c, (_, allele) in zip(cols, alleles)]
+        except ValueError:
+            raise ValueError("Some alleles were not present in the genotypes")
+    allele_arr = np.asarray(allele_arr, dtype=np.int64).reshape(-1)
+    if as_bool:
+        # the reference builds allele_arr with dtype=bool (haplotypes.py:1398)
+        allele_arr = np.minimum(allele_arr, 1)
+    lens = np.fromiter((len(x) for x in idxs), dtype=np.int64, count=len(idxs))
+    hap_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat = np.concatenate(idxs).astype(np.int64) if len(idxs) and hap_off[-1] else np.zeros(0, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64).reshape(-1)
+    ref_label = np.repeat(ancestries.astype(np.int64), lens) if ancestry else None
+    plan = plan_from_refs(cols[flat], allele_arr[flat], hap_off, gts.data.shape[1], ref_label)
+    return (plan, never) if unknown_label == "never" else plan

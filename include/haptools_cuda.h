@@ -1,0 +1,203 @@
+/*
+ * haptools_cuda.h -- C ABI of libhaptools_cuda.so (B200 / sm_100a)
+ *
+ * The drop-in boundary for ONE hot path of CAST-genomics/haptools: the haplotype
+ * transform.  The reference has no FFI seam for this path (it is ~75 lines of numpy);
+ * the entry points below are what a ctypes binding inside the reference's four
+ * transform methods binds instead of the numpy body:
+ *
+ *   Haplotypes.transform          haptools/data/haplotypes.py:1339-1413
+ *   Haplotype.transform           haptools/data/haplotypes.py:463-511
+ *   HaplotypesAncestry.transform  haptools/transform.py:91-149
+ *   HaplotypeAncestry.transform   haptools/transform.py:31-68
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no C++/torch types.  All data pointers are DEVICE
+ *     pointers unless the parameter name starts with `h_`.  The caller owns every
+ *     buffer (the Python host layer allocates them as torch tensors); the library keeps
+ *     no state between calls except the thread-local last-error string.
+ *   - Every launcher is asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ *     the legacy default stream) and thread-safe.
+ *   - Return value: HT_OK (0) or an HT_ERR_* code; ht_last_error() then describes it.
+ *   - Strides are in BYTES.
+ *
+ * Data model
+ *   key      one distinct (variant column, allele index[, ancestry label]) triple that at
+ *            least one haplotype references; the reference's `alleles` dict entry
+ *            (haplotypes.py:1375-1386).  The planner numbers keys so that keys of the
+ *            same variant are consecutive (CSR `var_key_off`), which lets the pack kernel
+ *            read each genotype column exactly once.
+ *   plane    the bit vector over samples of one key on one chromosome copy (strand):
+ *            bit = (GT[s, col, strand] == allele) [& (ANC[s, col, strand] == label)],
+ *            i.e. one column of the reference's `equality_arr` (haplotypes.py:1404,
+ *            transform.py:137,146) stored as 1 bit instead of 1 byte.
+ *   layout   planes are tile-major:  planes[tile][key][word 0..31][strand 0..1]  (uint32),
+ *            a tile being HT_TILE_SAMPLES = 1024 consecutive samples; bit b of word w of
+ *            tile t is sample t*1024 + w*32 + b.  Bits of samples >= n_samples are 0.
+ *            One (tile, key) record is 256 contiguous bytes.
+ */
+#ifndef HAPTOOLS_CUDA_H
+#define HAPTOOLS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HT_ABI_VERSION 4
+
+#define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
+#define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
+#define HT_RECORD_WORDS 64   /* uint32 per (tile, key) record     */
+
+#define HT_OK 0
+#define HT_ERR_BAD_ARG 1     /* NULL pointer, negative size, misaligned workspace ... */
+#define HT_ERR_CUDA 2        /* a CUDA runtime call or launch failed                  */
+#define HT_ERR_UNSUPPORTED 3 /* layout / size outside what the kernels handle         */
+
+/* bits of the optional `flags` word written by the pack kernels (QC side channel:
+ * Genotypes.check_missing, haptools/data/genotypes.py:444-485) */
+#define HT_FLAG_MISSING 1u      /* some referenced GT value >= 254                     */
+#define HT_FLAG_NON_BIALLELIC 2u /* some referenced GT value in 2..253                 */
+
+/* which pack kernel ht_pack_u8 should use; HT_PACK_AUTO picks from the strides */
+#define HT_PACK_AUTO 0
+#define HT_PACK_GENERIC 1      /* any strides: byte loads + __ballot_sync             */
+#define HT_PACK_VARIANT_MAJOR 2 /* samples contiguous along a variant row (VCF reader
+                                   layout, genotypes.py:183-186,210): 128-bit loads   */
+#define HT_PACK_SAMPLE_MAJOR 3  /* variants contiguous along a sample row (PGEN reader
+                                   layout, genotypes.py:1346-1352): 128-bit loads +
+                                   bytewise bit accumulation down the sample rows     */
+
+/* direction of ht_copy2d */
+#define HT_COPY_H2D 1
+#define HT_COPY_D2H 2
+#define HT_COPY_D2D 3
+
+/* ABI version of the loaded library (== HT_ABI_VERSION of the header it was built with). */
+int ht_version(void);
+
+/* Message for the last non-zero return on the calling thread ("" if none). */
+const char* ht_last_error(void);
+
+/* Number of plane tiles for n_samples, and bytes of the plane workspace for n_keys keys. */
+int64_t ht_num_tiles(int64_t n_samples);
+size_t ht_plane_bytes(int64_t n_samples, int64_t n_keys);
+
+/*
+ * K1 -- pack.  Replaces the column gather `gts.subset(variants=...)`
+ * (haplotypes.py:1388 -> genotypes.py:440) and `np.equal(allele_arr, gts.data[:, :, :2])`
+ * (haplotypes.py:1404; transform.py:137) and, when `anc` is given,
+ * `gts.ancestry[:, idxs] == ancestries[i]` (transform.py:146).
+ *
+ *   gt            genotype bytes (uint8 or numpy bool), element (s, v, c) at
+ *                 gt + s*gt_s_samp + v*gt_s_var + c*gt_s_strand, c in {0,1}; never copied.
+ *   anc           local-ancestry label bytes with its own strides, or NULL.
+ *   var_col[V]    column (index along the variant axis of gt/anc) of each distinct
+ *                 referenced variant.
+ *   var_key_off[V+1]  CSR: keys var_key_off[v] .. var_key_off[v+1]-1 belong to var_col[v].
+ *   key_allele[A] allele index each key matches against (`alleles.index(allele)`,
+ *                 haplotypes.py:1395; `int(allele != REF)`, transform.py:130).
+ *   key_label[A]  ancestry label of each key (NULL iff anc is NULL).
+ *   col_var[n_cols]  optional (may be NULL) dense inverse of var_col: index into var_col of
+ *                 each column of gt, or -1 for columns no haplotype references.  Needed
+ *                 by the sample-major kernel only (it walks whole rows of gt); without it
+ *                 HT_PACK_AUTO falls back to the generic kernel for that layout.
+ *   planes        workspace of ht_plane_bytes(n_samples, A) bytes, 16-byte aligned;
+ *                 fully overwritten.
+ *   flags         optional (may be NULL) uint32 that the kernel ORs HT_FLAG_* bits into.
+ *   mode          HT_PACK_*.
+ */
+int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t gt_s_strand,
+               const uint8_t* anc, int64_t anc_s_samp, int64_t anc_s_var,
+               int64_t anc_s_strand, int64_t n_samples, const uint32_t* var_col,
+               const uint32_t* var_key_off, const uint8_t* key_allele,
+               const uint8_t* key_label, int64_t n_vars, int64_t n_keys,
+               const int32_t* col_var, int64_t n_cols, uint32_t* planes, uint32_t* flags,
+               int mode, void* stream);
+
+/*
+ * K1 for pgenlib chunk buffers (GenotypesPLINK._iterate, genotypes.py:1373-1402):
+ * `alleles` is the int32 matrix (chunk_rows, 2*n_samples) that
+ * PgenReader.read_alleles_list fills -- row r = one variant, element 2*s + c, -9 = missing
+ * (never matches, like the 255 the reference turns it into at genotypes.py:1388-1390).
+ * var_col[] are ROW indices into this chunk; key ids are var_key_off-relative as in
+ * ht_pack_u8, offset by `key_base` so that consecutive chunks fill one plane workspace
+ * of `n_keys_total` keys.
+ */
+int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_samples,
+                const uint32_t* var_col, const uint32_t* var_key_off,
+                const uint8_t* key_allele, int64_t n_vars, int64_t key_base,
+                int64_t n_keys_total, uint32_t* planes, uint32_t* flags, void* stream);
+
+/*
+ * K2 -- transform.  Replaces the per-haplotype loop
+ * `hap_gts.data[:, i] = np.all(equality_arr[:, idxs[i]], axis=1)` (haplotypes.py:1411-1412;
+ * with ancestry folded into the keys also transform.py:144-148).
+ *
+ *   hap_off[H+1], hap_key[K]  CSR of key indices per haplotype (`idxs`, haplotypes.py:1380).
+ *   out     uint8 matrix: element (s, h, c) at out + s*out_s_samp + 2*h + c receives exactly
+ *           0x00 or 0x01 (numpy bool bytes).  A haplotype without keys yields 0x01
+ *           (np.all over an empty axis).  out_s_samp >= 2*H.  Rows >= n_samples are not
+ *           touched.
+ */
+int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                    const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
+                    uint8_t* out, int64_t out_s_samp, void* stream);
+
+/*
+ * K2, bit-packed result: out_bits has the plane layout with haplotypes in place of keys
+ * (out_bits[tile][hap][word][strand]); 1/8 of the bytes of the uint8 form, used for the
+ * optional all-gather across sample shards and for device-side consumers.  Feeding it
+ * back through ht_transform_u8 with an identity CSR unpacks it.
+ */
+int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                      const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
+                      uint32_t* out_bits, void* stream);
+
+/*
+ * Per-haplotype allele counts of a bit-packed result (popcount over samples and strands)
+ * -- the numerator of GenotypesVCF.check_maf (genotypes.py:559-625) for `--maf`.
+ * counts[h] (uint64) is overwritten.
+ */
+int ht_count_bits(const uint32_t* bits, int64_t n_samples, int64_t n_haps, uint64_t* counts,
+                  void* stream);
+
+/*
+ * Deterministic synthetic genotypes for the benchmark configs (not part of the
+ * reference): fills `gt` (same addressing as ht_pack_u8, all three bytes of a
+ * phase-column layout are NOT touched beyond c in {0,1}) from a counter-based hash of
+ * (seed, sample, variant, strand); see haptools_b200/synth.py for the numpy restatement.
+ *   mode 0: iid Bernoulli(1/2) alleles
+ *   mode 1: "blocky": per 64-variant block each (sample, strand) copies one of 16 founder
+ *           haplotypes, so multi-variant haplotypes have non-trivial frequencies
+ *   missing_per_64k: expected number of 255 calls per 65536 genotype bytes.
+ */
+int ht_synth_gt(uint8_t* gt, int64_t s_samp, int64_t s_var, int64_t s_strand,
+                int64_t n_samples, int64_t n_vars, int64_t sample_offset, uint64_t seed,
+                int mode, uint32_t missing_per_64k, void* stream);
+
+/* Synthetic local-ancestry labels (same addressing): piecewise constant along variants in
+ * tracts of `tract_len` variants with a per-(sample, strand) phase, label uniform in
+ * [0, n_pops). */
+int ht_synth_ancestry(uint8_t* anc, int64_t s_samp, int64_t s_var, int64_t s_strand,
+                      int64_t n_samples, int64_t n_vars, int64_t sample_offset, uint64_t seed,
+                      uint32_t n_pops, uint32_t tract_len, void* stream);
+
+/*
+ * Host <-> device plumbing for the Python host layer (GenotypesPLINK-style chunked input,
+ * haptools/data/genotypes.py:1353-1406, and strided result read-back): a pitched 2-D copy
+ * (cudaMemcpy2DAsync; `kind` = HT_COPY_*) and page-locking of an existing host range, so that
+ * numpy buffers can be DMA'd without a staging copy.  h_ptr is a HOST pointer.
+ */
+int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+              int64_t width_bytes, int64_t height, int kind, void* stream);
+int ht_host_register(void* h_ptr, size_t bytes);
+int ht_host_unregister(void* h_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAPTOOLS_CUDA_H */
