@@ -18,8 +18,8 @@
 //   variant-major  samples contiguous (VCF reader layout): 128-bit coalesced loads, SWAR byte
 //                  compare, carry-free multiply to gather match bits, 4-lane shuffle merge
 //   sample-major   variants contiguous (PGEN reader layout / C-contiguous arrays): each thread
-//                  streams 8-byte column chunks down 128 sample rows, accumulating match
-//                  bits bytewise (acc = acc>>1 | flags), then byte-transposes with PRMT
+//                  streams a 4-byte column chunk down the sample rows, accumulating match
+//                  bits bytewise, then byte-transposes with PRMT (details at the kernel)
 //
 // Roofline: HBM read of n*V*2 genotype bytes (+ ancestry) and write of A*2*ceil(n/32)*4.
 #include "ht_common.cuh"
@@ -28,7 +28,6 @@ namespace ht {
 
 constexpr int kPackWarps = 8;
 constexpr int kPackThreads = kPackWarps * 32;
-constexpr int kSmCols = 128;  // columns per CTA of the sample-major kernel
 
 struct PackArgs {
     const uint8_t* gt;
@@ -71,9 +70,13 @@ __device__ __forceinline__ uint32_t qc_flags4(uint32_t x) {
 
 __device__ __forceinline__ void publish_flags(uint32_t* flags, uint32_t f) {
     if (!flags) return;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) f |= __shfl_xor_sync(0xffffffffu, f, d);
-    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+    // lanes may have exited or diverged: reduce over whoever is here
+    const unsigned m = __activemask();
+    f = __reduce_or_sync(m, f);
+    if ((threadIdx.x & 31) == __ffs(m) - 1 && f) {
+        // one atomic per warp at most, and none once the bits are already set
+        if (f & ~*reinterpret_cast<volatile uint32_t*>(flags)) atomicOr(flags, f);
+    }
 }
 
 // mask of the samples of word `word` of `tile` that exist
@@ -239,123 +242,226 @@ pack_vm_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
 }
 
 // -----------------------------------------------------------------------------------------
-// sample-major kernel (s_strand == 1, s_var == 2): CTA per (tile, 128 columns); lane = 4
-// columns (8 bytes of every sample row), warp = 4 words (128 samples)
+// sample-major kernel (s_strand == 1, s_var == 2)
+//   CTA  = (tile of 1024 samples) x (512 consecutive columns = 1 KB of every sample row)
+//   warp = 64 of those columns, all 1024 rows in 8 groups of 128 rows (4 words)
+//   lane = 2 columns = 4 bytes of every row {col0.s0, col0.s1, col1.s0, col1.s1}
+// Per row the lane folds its 4 bytes into 4 byte-wide shift registers (one per byte column);
+// after 8 rows each byte holds 8 sample bits, after 32 rows a 4x4 byte transpose (PRMT) gives
+// one 32-sample word per byte column.  Per 128 rows every (key, lane) pair stores one full
+// 32-byte sector of the key's record.
+//
+// Columns whose keys are just alleles {0, 1} without ancestry take the single-pass path: the
+// allele-1 plane is the bytes' low bit, the allele-0 plane its complement, both masked by an
+// "invalid" plane (byte >= 2: missing or multi-allelic call) that is only built for 8-row
+// blocks that contain such a byte -- exact for any input, 3 ALU ops per 4 bytes when clean.
+// Other columns (multi-allelic keys, ancestry labels) take one SWAR-compare pass per key.
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint2 load_cols8(const uint8_t* p, int ncols) {
-    if (ncols >= 4) return __ldg(reinterpret_cast<const uint2*>(p));
-    uint32_t w[2] = {0u, 0u};
-    for (int i = 0; i < 2 * ncols; ++i) w[i >> 2] |= (uint32_t)p[i] << (8 * (i & 3));
-    return make_uint2(w[0], w[1]);
+constexpr int kSmLaneCols = 2;
+constexpr int kSmWarpCols = 32 * kSmLaneCols;            // 64
+constexpr int kSmCtaCols = kPackWarps * kSmWarpCols;     // 512
+
+__device__ __forceinline__ uint32_t load_cols4(const uint8_t* p, int ncols) {
+    if (ncols >= 2) return __ldg(reinterpret_cast<const uint32_t*>(p));
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+}
+
+// bytes b of G[0..3] -> word b (G[q] holds rows 8q..8q+7 of the 4 byte columns)
+__device__ __forceinline__ void byte_transpose4(const uint32_t (&G)[4], uint32_t (&w)[4]) {
+    const uint32_t t0 = prmt(G[0], G[1], 0x5140), t1 = prmt(G[2], G[3], 0x5140);
+    const uint32_t t2 = prmt(G[0], G[1], 0x7362), t3 = prmt(G[2], G[3], 0x7362);
+    w[0] = prmt(t0, t1, 0x5410);
+    w[1] = prmt(t0, t1, 0x7632);
+    w[2] = prmt(t2, t3, 0x5410);
+    w[3] = prmt(t2, t3, 0x7632);
+}
+
+// One 32-byte sector of a key's record: words 4*grp .. 4*grp+3, both strands, of byte-column
+// pair i, read back from the thread's private staging column.  stage[w4*8 + k] = value word
+// k of word w4, stage[w4*8 + 4 + k] = invalid word.
+__device__ __forceinline__ void store_sector(uint2* rec4, const uint32_t* stage, int i, bool invert,
+                                             const uint32_t (&vm)[4]) {
+    uint32_t o[8];
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t v = stage[(w4 * 8 + 2 * i + c) * kPackThreads];
+            const uint32_t z = stage[(w4 * 8 + 4 + 2 * i + c) * kPackThreads];
+            o[2 * w4 + c] = (invert ? ~v : v) & ~z & vm[w4];
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(rec4);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 template <bool kAnc>
-__global__ void __launch_bounds__(kPackThreads)
+__global__ void __launch_bounds__(kPackThreads, 4)
 pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    // thread-private staging (column = thread): keeps the per-word loop rolled, i.e. the code
+    // small enough for the instruction cache
+    __shared__ uint32_t s_stage[32 * kPackThreads];  // 32 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_cblocks;
-    const int64_t col0 = (cblock0 + blockIdx.x % n_cblocks) * kSmCols + 4 * lane;
-    const int ncols = (int)min((int64_t)4, a.n_cols - col0);  // may be <= 0
+    const int64_t col0 =
+        ((cblock0 + blockIdx.x % n_cblocks) * kPackWarps + warp) * kSmWarpCols + kSmLaneCols * lane;
+    const int ncols = (int)min((int64_t)kSmLaneCols, a.n_cols - col0);  // may be <= 0
     if (ncols <= 0) return;
 
-    // which of my 4 columns are referenced, and their key ranges
-    uint32_t kb[4], nk[4];
-    uint32_t rounds = 0, refmask[2] = {0u, 0u};
+    // which of my columns are referenced, and by which keys
+    uint32_t kb[2] = {0u, 0u}, nk[2] = {0u, 0u};
+    int k_ref[2] = {-1, -1}, k_alt[2] = {-1, -1};  // key of allele 0 / 1 (single-pass path)
+    bool simple = !kAnc;
+    uint32_t refmask = 0u, rounds = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        kb[i] = 0;
-        nk[i] = 0;
+    for (int i = 0; i < 2; ++i) {
         if (i < ncols) {
             const int32_t v = __ldg(a.col_var + col0 + i);
             if (v >= 0) {
                 kb[i] = __ldg(a.var_key_off + v);
                 nk[i] = __ldg(a.var_key_off + v + 1) - kb[i];
-                refmask[i >> 1] |= 0xffffu << (16 * (i & 1));
+                refmask |= 0xffffu << (16 * i);
+                rounds = max(rounds, nk[i]);
+                if (!kAnc) {
+                    // keys of a variant are sorted by allele and distinct
+                    for (uint32_t k = 0; k < min(nk[i], 2u); ++k) {
+                        const uint32_t al = __ldg(a.key_allele + kb[i] + k);
+                        if (al == 0) k_ref[i] = (int)(kb[i] + k);
+                        else if (al == 1) k_alt[i] = (int)(kb[i] + k);
+                        else simple = false;
+                    }
+                    simple = simple && nk[i] <= 2;
+                }
             }
         }
-        rounds = max(rounds, nk[i]);
     }
     if (rounds == 0) return;
 
     const uint8_t* g = a.gt + col0 * 2;
     const uint8_t* l = kAnc ? a.anc + col0 * 2 : nullptr;
-    const int64_t s_warp = tile * kTileSamples + 128 * warp;
+    uint32_t* stage = s_stage + threadIdx.x;
     uint32_t fl = 0;
 
-    for (uint32_t r = 0; r < rounds; ++r) {
-        // per-byte patterns of this round's key of each column
-        uint32_t pb[4] = {0u, 0u, 0u, 0u}, lb[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+    for (int grp = 0; grp < 8; ++grp) {
+        const int64_t s_grp = tile * kTileSamples + 128 * grp;
+        if (s_grp >= a.n) break;
+        uint32_t vm[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (r < nk[i]) {
-                pb[i] = __ldg(a.key_allele + kb[i] + r);
-                if (kAnc) lb[i] = __ldg(a.key_label + kb[i] + r);
-            }
-        }
-        const uint2 pat = make_uint2((pb[0] | (pb[1] << 16)) * 0x0101u, (pb[2] | (pb[3] << 16)) * 0x0101u);
-        const uint2 lpat = make_uint2((lb[0] | (lb[1] << 16)) * 0x0101u, (lb[2] | (lb[3] << 16)) * 0x0101u);
+        for (int k = 0; k < 4; ++k) vm[k] = valid_mask(a.n, tile, 4 * grp + k);
 
-        // res[w4][2*i + c]: word (4*warp + w4) of column i, strand c
-        uint32_t res[4][8];
+        if (simple) {
+            // all 128 rows exist and both of my columns do: no per-row checks, and the 32 row
+            // loads of a word are issued back to back (32 independent loads in flight)
+            const bool full = (s_grp + 128 <= a.n) && ncols == kSmLaneCols;
+            const uint8_t* p = g + s_grp * a.gs;
+#pragma unroll 1
+            for (int w4 = 0; w4 < 4; ++w4) {
+                uint32_t x[32];
+                if (full) {
 #pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-            uint2 G[4];
+                    for (int rr = 0; rr < 32; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int64_t s_first = s_warp + 32 * w4 + 8 * q;
-                uint2 x[8], c[8];
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    const int64_t s = s_first + rr;
-                    x[rr] = make_uint2(0u, 0u);
-                    if (s < a.n) x[rr] = load_cols8(g + s * a.gs, ncols);
-                    if (kAnc) {
-                        c[rr] = make_uint2(0u, 0u);
-                        if (s < a.n) c[rr] = load_cols8(l + s * a.as, ncols);
+                    for (int rr = 0; rr < 32; ++rr, p += a.gs) {
+                        x[rr] = 0u;
+                        if (s_grp + 32 * w4 + rr < a.n) x[rr] = load_cols4(p, ncols);
                     }
                 }
-                uint2 acc = make_uint2(0u, 0u);
+                uint32_t GA[4], GZ[4];
+                bool any_dirty = false;
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) {
-                    uint2 f = make_uint2(eq_bytes_msb(x[rr].x, pat.x), eq_bytes_msb(x[rr].y, pat.y));
-                    if (kAnc) {
-                        f.x &= eq_bytes_msb(c[rr].x, lpat.x);
-                        f.y &= eq_bytes_msb(c[rr].y, lpat.y);
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t acc = 0u, d = 0u;
+#pragma unroll
+                    for (int rr = 7; rr >= 0; --rr) {  // row rr ends at bit rr of its byte
+                        acc = (acc << 1) + (x[8 * q + rr] & 0x01010101u);
+                        d |= x[8 * q + rr];
                     }
-                    // row rr enters at bit 7 of its byte and ends at bit rr after 7 - rr shifts
-                    acc.x = (acc.x >> 1) | f.x;
-                    acc.y = (acc.y >> 1) | f.y;
-                    if (r == 0 && a.flags)
-                        fl |= qc_flags4(x[rr].x & refmask[0]) | qc_flags4(x[rr].y & refmask[1]);
-                }
-                G[q] = acc;
-            }
-            // 4x4 byte transposes: byte b of G[q] (8 samples of byte-column b) -> word per column
-            const uint32_t vm = valid_mask(a.n, tile, 4 * warp + w4);
-            {
-                const uint32_t t0 = prmt(G[0].x, G[1].x, 0x5140), t1 = prmt(G[2].x, G[3].x, 0x5140);
-                const uint32_t t2 = prmt(G[0].x, G[1].x, 0x7362), t3 = prmt(G[2].x, G[3].x, 0x7362);
-                res[w4][0] = prmt(t0, t1, 0x5410) & vm;
-                res[w4][1] = prmt(t0, t1, 0x7632) & vm;
-                res[w4][2] = prmt(t2, t3, 0x5410) & vm;
-                res[w4][3] = prmt(t2, t3, 0x7632) & vm;
-            }
-            {
-                const uint32_t t0 = prmt(G[0].y, G[1].y, 0x5140), t1 = prmt(G[2].y, G[3].y, 0x5140);
-                const uint32_t t2 = prmt(G[0].y, G[1].y, 0x7362), t3 = prmt(G[2].y, G[3].y, 0x7362);
-                res[w4][4] = prmt(t0, t1, 0x5410) & vm;
-                res[w4][5] = prmt(t0, t1, 0x7632) & vm;
-                res[w4][6] = prmt(t2, t3, 0x5410) & vm;
-                res[w4][7] = prmt(t2, t3, 0x7632) & vm;
-            }
-        }
-        // one full 32-byte sector per (key, warp): words 4*warp .. 4*warp+3, both strands
+                    GA[q] = acc;
+                    GZ[q] = 0u;
+                    if (d & 0xfefefefeu) {  // some byte >= 2: build the invalid plane of this block
+                        any_dirty = true;
+                        uint32_t z = 0u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (r < nk[i]) {
-                uint4* dst = reinterpret_cast<uint4*>(record(a, tile, kb[i] + r) + 4 * warp);
-                dst[0] = make_uint4(res[0][2 * i], res[0][2 * i + 1], res[1][2 * i], res[1][2 * i + 1]);
-                dst[1] = make_uint4(res[2][2 * i], res[2][2 * i + 1], res[3][2 * i], res[3][2 * i + 1]);
+                        for (int rr = 7; rr >= 0; --rr) {
+                            const uint32_t v = x[8 * q + rr];
+                            const uint32_t t = (((v & 0x7e7e7e7eu) + 0x7e7e7e7eu) | v) & 0x80808080u;
+                            z = (z << 1) + (t >> 7);
+                        }
+                        GZ[q] = z;
+                        if (a.flags) {
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) fl |= qc_flags4(x[8 * q + rr] & refmask);
+                        }
+                    }
+                }
+                uint32_t w[4], z[4] = {0u, 0u, 0u, 0u};
+                byte_transpose4(GA, w);
+                if (any_dirty) byte_transpose4(GZ, z);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    stage[(w4 * 8 + k) * kPackThreads] = w[k];
+                    stage[(w4 * 8 + 4 + k) * kPackThreads] = z[k];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (k_alt[i] >= 0) store_sector(record(a, tile, (uint32_t)k_alt[i]) + 4 * grp, stage, i, false, vm);
+                if (k_ref[i] >= 0) store_sector(record(a, tile, (uint32_t)k_ref[i]) + 4 * grp, stage, i, true, vm);
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t r = 0; r < rounds; ++r) {
+                uint32_t pb[2] = {0u, 0u}, lb[2] = {0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (r < nk[i]) {
+                        pb[i] = __ldg(a.key_allele + kb[i] + r);
+                        if (kAnc) lb[i] = __ldg(a.key_label + kb[i] + r);
+                    }
+                }
+                const uint32_t pat = (pb[0] | (pb[1] << 16)) * 0x0101u;
+                const uint32_t lpat = (lb[0] | (lb[1] << 16)) * 0x0101u;
+#pragma unroll 1
+                for (int w4 = 0; w4 < 4; ++w4) {
+                    uint32_t G[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t s_first = s_grp + 32 * w4 + 8 * q;
+                        uint32_t x[8], c[8];
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            x[rr] = 0u;
+                            c[rr] = 0u;
+                            if (s_first + rr < a.n) {
+                                x[rr] = load_cols4(g + (s_first + rr) * a.gs, ncols);
+                                if (kAnc) c[rr] = load_cols4(l + (s_first + rr) * a.as, ncols);
+                            }
+                        }
+                        uint32_t acc = 0u;
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            uint32_t f = eq_bytes_msb(x[rr], pat);
+                            if (kAnc) f &= eq_bytes_msb(c[rr], lpat);
+                            acc = (acc >> 1) | f;  // row rr enters at bit 7, ends at bit rr
+                            if (r == 0 && a.flags) fl |= qc_flags4(x[rr] & refmask);
+                        }
+                        G[q] = acc;
+                    }
+                    uint32_t w[4];
+                    byte_transpose4(G, w);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        stage[(w4 * 8 + k) * kPackThreads] = w[k];
+                        stage[(w4 * 8 + 4 + k) * kPackThreads] = 0u;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (r < nk[i]) store_sector(record(a, tile, kb[i] + r) + 4 * grp, stage, i, false, vm);
+                }
             }
         }
     }
@@ -428,9 +534,9 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
 
     const bool vm_ok = gt_s_strand == 1 && gt_s_samp == 2 && aligned(gt, gt_s_var, 16) &&
                        (!anc || (anc_s_strand == 1 && anc_s_samp == 2 && aligned(anc, anc_s_var, 16)));
-    const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 8) && col_var &&
+    const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 4) && col_var &&
                        n_cols > 0 &&
-                       (!anc || (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 8)));
+                       (!anc || (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 4)));
     if (mode == HT_PACK_AUTO)
         mode = vm_ok ? HT_PACK_VARIANT_MAJOR : (sm_ok ? HT_PACK_SAMPLE_MAJOR : HT_PACK_GENERIC);
 
@@ -448,10 +554,10 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                        : launch_tiled(pack_vm_kernel<false>, a, n_vblocks, 0, false, st);
         case HT_PACK_SAMPLE_MAJOR: {
             if (!sm_ok) {
-                set_error("sample-major pack needs s_strand=1, s_var=2, 8-byte aligned rows and col_var");
+                set_error("sample-major pack needs s_strand=1, s_var=2, 4-byte aligned rows and col_var");
                 return HT_ERR_UNSUPPORTED;
             }
-            const int64_t n_cblocks = (n_cols + kSmCols - 1) / kSmCols;
+            const int64_t n_cblocks = (n_cols + kSmCtaCols - 1) / kSmCtaCols;
             return anc ? launch_tiled(pack_sm_kernel<true>, a, n_cblocks, 0, true, st)
                        : launch_tiled(pack_sm_kernel<false>, a, n_cblocks, 0, true, st);
         }

@@ -29,8 +29,9 @@ constexpr int kHapBlock = 128;      // haplotypes per CTA
 constexpr int kHapsPerWarp = 16;    // -> 32 result bits (16 haps x 2 strands) per sample
 constexpr int kWarps = kHapBlock / kHapsPerWarp;  // 8
 constexpr int kThreads = kWarps * 32;             // 256
-constexpr int kStageKeys = 3072;    // key indices staged per CTA (12 KB); longer lists are
-                                    // read straight from global memory
+constexpr int kStageKeys = 3072;    // key indices staged per CTA (12 KB, each haplotype's list
+                                    // padded to a multiple of 4); longer blocks read their
+                                    // lists straight from global memory
 constexpr int kUPitch = kTileSamples + 4;  // +4 words: the 8 warps' rows land in distinct banks
 
 __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
@@ -46,17 +47,18 @@ __device__ __forceinline__ void st_stream_v4(uint8_t* p, uint4 v) {
 }
 
 // AND of the (tile, key) records of one haplotype, for this lane's word; both strands.
-template <bool kStaged>
-__device__ __forceinline__ uint2 and_keys(const uint2* __restrict__ tile_rec,  // + lane
-                                          const uint32_t* __restrict__ keys,   // smem or global
-                                          uint32_t kb, uint32_t ke) {
+// Unstaged variant (key list read from global memory): 4 keys per round trip, the last batch
+// repeats the final key (AND is idempotent) instead of a scalar tail loop.  Loops are
+// deliberately NOT unrolled: the whole kernel has to stay inside the instruction cache.
+__device__ __forceinline__ uint2 and_keys_global(const uint2* __restrict__ tile_rec,  // + lane
+                                                 const uint32_t* __restrict__ keys, uint32_t kb,
+                                                 uint32_t ke) {
     uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu;
-    uint32_t j = kb;
-    for (; j + 4 <= ke; j += 4) {
-        const uint32_t k0 = kStaged ? keys[j] : __ldg(keys + j);
-        const uint32_t k1 = kStaged ? keys[j + 1] : __ldg(keys + j + 1);
-        const uint32_t k2 = kStaged ? keys[j + 2] : __ldg(keys + j + 2);
-        const uint32_t k3 = kStaged ? keys[j + 3] : __ldg(keys + j + 3);
+    const uint32_t last = ke - 1;
+#pragma unroll 1
+    for (uint32_t j = kb; j < ke; j += 4) {
+        const uint32_t k0 = __ldg(keys + j), k1 = __ldg(keys + min(j + 1, last));
+        const uint32_t k2 = __ldg(keys + min(j + 2, last)), k3 = __ldg(keys + min(j + 3, last));
         const uint2 v0 = ld_plane(tile_rec + (size_t)k0 * kTileWords);
         const uint2 v1 = ld_plane(tile_rec + (size_t)k1 * kTileWords);
         const uint2 v2 = ld_plane(tile_rec + (size_t)k2 * kTileWords);
@@ -64,27 +66,99 @@ __device__ __forceinline__ uint2 and_keys(const uint2* __restrict__ tile_rec,  /
         r0 &= (v0.x & v1.x) & (v2.x & v3.x);
         r1 &= (v0.y & v1.y) & (v2.y & v3.y);
     }
-    for (; j < ke; ++j) {
-        const uint32_t k0 = kStaged ? keys[j] : __ldg(keys + j);
-        const uint2 v0 = ld_plane(tile_rec + (size_t)k0 * kTileWords);
-        r0 &= v0.x;
-        r1 &= v0.y;
-    }
     return make_uint2(r0, r1);
+}
+
+// Staged key quads: bits 31/30 of the FIRST key of a quad carry flags.
+constexpr uint32_t kQuadLast = 0x80000000u;  // last quad of its haplotype: emit the result
+constexpr uint32_t kQuadSkip = 0x40000000u;  // stands for a haplotype without alleles
+constexpr uint32_t kKeyMask = 0x3fffffffu;
+
+struct Batch {  // two quads = 8 plane records in flight
+    uint2 v[8];
+    uint32_t f0, f1;  // flag words of the two quads
+};
+
+__device__ __forceinline__ void load_batch(const uint2* __restrict__ tile_rec,
+                                           const uint4* __restrict__ quads, uint32_t q,
+                                           uint32_t q_last, Batch& b) {
+    const uint4 ka = quads[q], kb = quads[min(q + 1, q_last)];
+    b.f0 = ka.x;
+    b.f1 = kb.x;
+    b.v[0] = ld_plane(tile_rec + (size_t)(ka.x & kKeyMask) * kTileWords);
+    b.v[1] = ld_plane(tile_rec + (size_t)ka.y * kTileWords);
+    b.v[2] = ld_plane(tile_rec + (size_t)ka.z * kTileWords);
+    b.v[3] = ld_plane(tile_rec + (size_t)ka.w * kTileWords);
+    b.v[4] = ld_plane(tile_rec + (size_t)(kb.x & kKeyMask) * kTileWords);
+    b.v[5] = ld_plane(tile_rec + (size_t)kb.y * kTileWords);
+    b.v[6] = ld_plane(tile_rec + (size_t)kb.z * kTileWords);
+    b.v[7] = ld_plane(tile_rec + (size_t)kb.w * kTileWords);
+}
+
+__device__ __forceinline__ void consume_quad(const uint2* v, uint32_t flags, uint32_t& r0,
+                                             uint32_t& r1, uint2*& park) {
+    if (!(flags & kQuadSkip)) {
+        r0 &= (v[0].x & v[1].x) & (v[2].x & v[3].x);
+        r1 &= (v[0].y & v[1].y) & (v[2].y & v[3].y);
+    }
+    if (flags & kQuadLast) {  // warp-uniform
+        *park = make_uint2(r0, r1);
+        park += 32;
+        r0 = r1 = 0xffffffffu;
+    }
+}
+
+// Staged AND phase of one warp.  The key lists of its 16 haplotypes are consecutive quads in
+// shared memory (each list padded to a multiple of 4 by repeating its last key -- AND is
+// idempotent; a haplotype without alleles gets one "skip" quad), so the warp walks them as
+// ONE stream, two quads (8 records of 256 B) per step, always with the next step's 8 reads
+// already in flight; a haplotype's result is emitted when its last quad is consumed.
+__device__ __forceinline__ void and_phase_staged(const uint2* __restrict__ tile_rec,
+                                                 const uint4* __restrict__ quads, uint32_t q,
+                                                 uint32_t q_end, uint2* park) {
+    if (q >= q_end) return;
+    uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu;
+    const uint32_t q_last = q_end - 1;
+    Batch A, B;
+    load_batch(tile_rec, quads, q, q_last, A);
+#pragma unroll 1
+    while (true) {
+        if (q + 2 < q_end) load_batch(tile_rec, quads, q + 2, q_last, B);
+        consume_quad(A.v, A.f0, r0, r1, park);
+        if (q + 1 < q_end) consume_quad(A.v + 4, A.f1, r0, r1, park);
+        q += 2;
+        if (q >= q_end) break;
+        if (q + 2 < q_end) load_batch(tile_rec, quads, q + 2, q_last, A);
+        consume_quad(B.v, B.f0, r0, r1, park);
+        if (q + 1 < q_end) consume_quad(B.v + 4, B.f1, r0, r1, park);
+        q += 2;
+        if (q >= q_end) break;
+    }
+}
+
+__device__ __forceinline__ uint4 expand16(uint32_t bits) {
+    uint4 o;
+    o.x = spread4(bits & 15u);
+    o.y = spread4((bits >> 4) & 15u);
+    o.z = spread4((bits >> 8) & 15u);
+    o.w = spread4((bits >> 12) & 15u);
+    return o;
 }
 
 // out_vec: 16 -> every full 8-haplotype group is stored with one 16-byte store (requires
 //          out and out_s_samp to be multiples of 16); 2 -> 2-byte stores only (any layout
 //          with even addresses); 1 -> byte stores.
 template <int kOutVec>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                     const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
                     int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0,
                     uint8_t* __restrict__ out, int64_t out_s_samp) {
-    __shared__ uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
-    __shared__ uint32_t s_keys[kStageKeys];     // 12 KB
-    __shared__ uint32_t s_off[kHapBlock + 1];
+    __shared__ __align__(16) uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
+    __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
+    __shared__ uint32_t s_off[kHapBlock + 1];                  // CSR offsets of the block
+    __shared__ uint32_t s_quad[kHapBlock + 1];                 // first quad of each haplotype
+    __shared__ uint32_t s_wsum[kHapBlock / 32];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -92,33 +166,93 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
     const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
     const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
 
-    // ---- stage the block's CSR slice -------------------------------------------------
+    // ---- stage the block's CSR slice: offsets, then each key list padded to quads ------
     for (int i = tid; i <= n_blk_haps; i += kThreads) s_off[i] = __ldg(hap_off + h0 + i);
     __syncthreads();
-    const uint32_t k_begin = s_off[0];
-    const uint32_t k_count = s_off[n_blk_haps] - k_begin;
-    const bool staged = k_count <= (uint32_t)kStageKeys;
-    if (staged) {
-        for (uint32_t i = tid; i < k_count; i += kThreads) s_keys[i] = __ldg(hap_key + k_begin + i);
+    if (tid < kHapBlock) {  // exclusive prefix sum of the quad counts of the block's haplotypes
+        const uint32_t nq = tid < n_blk_haps ? max(1u, (s_off[tid + 1] - s_off[tid] + 3u) >> 2) : 0u;
+        uint32_t inc = nq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        s_quad[tid] = inc - nq;  // within-warp exclusive
     }
     __syncthreads();
+    if (tid < kHapBlock) {
+        uint32_t base = 0;
+        for (int w = 0; w < warp; ++w) base += s_wsum[w];
+        s_quad[tid] += base;
+    }
+    if (tid == 0) s_quad[kHapBlock] = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
+    __syncthreads();
+    // n_keys == 0 means every haplotype is empty and `planes` may be NULL: never load
+    const int hl_begin = warp * kHapsPerWarp;
+    const int hl_end = min(hl_begin + kHapsPerWarp, n_blk_haps);
+    uint32_t* my_row = s_u + warp * kUPitch;
+    // every warp stages (and later consumes) the lists of its own 16 haplotypes: a contiguous
+    // slice of hap_key.  Raw copy first (independent coalesced loads, one round trip), into
+    // the warp's exchange row, which is free until the AND phase parks results in it.
+    const uint32_t w_kb = hl_begin < hl_end ? s_off[hl_begin] : 0u;
+    const uint32_t w_cnt = hl_begin < hl_end ? s_off[hl_end] - w_kb : 0u;
+    const bool staged = s_quad[kHapBlock] * 4u <= (uint32_t)kStageKeys && n_keys > 0 &&
+                        w_cnt <= (uint32_t)kTileSamples;
+    if (staged) {
+#pragma unroll 1
+        for (uint32_t j = lane; j < w_cnt; j += 128) {
+            const uint32_t* src = hap_key + w_kb + j;
+            const uint32_t k0 = __ldg(src);
+            const uint32_t k1 = j + 32 < w_cnt ? __ldg(src + 32) : 0u;
+            const uint32_t k2 = j + 64 < w_cnt ? __ldg(src + 64) : 0u;
+            const uint32_t k3 = j + 96 < w_cnt ? __ldg(src + 96) : 0u;
+            my_row[j] = k0;
+            if (j + 32 < w_cnt) my_row[j + 32] = k1;
+            if (j + 64 < w_cnt) my_row[j + 64] = k2;
+            if (j + 96 < w_cnt) my_row[j + 96] = k3;
+        }
+        __syncwarp();
+        // pad each list to whole quads (repeat its last key) and flag the quads
+#pragma unroll 1
+        for (int hl = hl_begin; hl < hl_end; ++hl) {
+            const uint32_t kb = s_off[hl] - w_kb, len = s_off[hl + 1] - s_off[hl];
+            const uint32_t base = 4u * s_quad[hl], padded = max(4u, (len + 3u) & ~3u);
+#pragma unroll 1
+            for (uint32_t j = lane; j < padded; j += 32) {
+                uint32_t key = len ? my_row[kb + min(j, len - 1)] : 0u;
+                if ((j & 3u) == 0u) key |= (j + 4 >= padded ? kQuadLast : 0u) | (len ? 0u : kQuadSkip);
+                s_keys[base + j] = key;
+            }
+        }
+    }
+    __syncwarp();
 
     // ---- 1. AND ----------------------------------------------------------------------
+    // results are parked in the warp's own slice of s_u (which is only reused for the
+    // exchange after the warp has read everything back): keeps the haplotype loop rolled
     const uint2* tile_rec =
         reinterpret_cast<const uint2*>(planes) + ((size_t)tile * (size_t)n_keys) * kTileWords + lane;
-    uint32_t a[32];
+    uint2* park = reinterpret_cast<uint2*>(my_row) + lane;
+    if (staged) {
+        if (hl_begin < hl_end)
+            and_phase_staged(tile_rec, reinterpret_cast<const uint4*>(s_keys), s_quad[hl_begin], s_quad[hl_end], park);
+    } else {
+#pragma unroll 1
+        for (int hl = hl_begin; hl < hl_end; ++hl) {
+            uint2 r = make_uint2(0xffffffffu, 0xffffffffu);
+            if (n_keys > 0) r = and_keys_global(tile_rec, hap_key, s_off[hl], s_off[hl + 1]);
+            park[(hl - hl_begin) * 32] = r;
+        }
+    }
+    uint32_t a[32];  // a[2*i + c] = haplotype i of this warp, strand c
 #pragma unroll
     for (int i = 0; i < kHapsPerWarp; ++i) {
-        const int hl = warp * kHapsPerWarp + i;
-        uint2 r = make_uint2(0u, 0u);
-        if (hl < n_blk_haps) {
-            const uint32_t kb = s_off[hl], ke = s_off[hl + 1];
-            r = staged ? and_keys<true>(tile_rec, s_keys, kb - k_begin, ke - k_begin)
-                       : and_keys<false>(tile_rec, hap_key, kb, ke);
-        }
+        const uint2 r = park[i * 32];
         a[2 * i] = r.x;
         a[2 * i + 1] = r.y;
     }
+    __syncwarp();
 
     // ---- 2. bits over samples -> bits over (haplotype, strand) ------------------------
     transpose32(a);
@@ -126,36 +260,44 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
     // ---- 3. exchange + expand + store --------------------------------------------------
     // sample 32*L + j of the tile is kept at slot 32*L + ((j + L) & 31): lanes write distinct
     // banks here, and the 16 words one warp reads below fall into 16 distinct banks.
-    uint32_t* my_u = s_u + warp * kUPitch + 32 * lane;
+    uint32_t* my_u = my_row + 32 * lane;
 #pragma unroll
     for (int j = 0; j < 32; ++j) my_u[(j + lane) & 31] = a[j];
     __syncthreads();
 
     const int half = lane & 1;        // low / high 16 bits of the word = haps 0-7 / 8-15
     const int b = (lane >> 1) & 7;    // which warp's 16 haplotypes
-    const int rsub = lane >> 4;       // 2 sample rows per warp-wide store
+    const int c0 = warp * 2 + (lane >> 4);  // sample row within each group of 16
     const int hl0 = b * kHapsPerWarp + half * 8;  // first haplotype (in block) of my 16 bytes
     const int n_my_haps = min(8, n_blk_haps - hl0);  // may be <= 0
     if (n_my_haps <= 0) return;  // no barrier below
     const int64_t s_base = tile * kTileSamples;
     const int rows = (int)min((int64_t)kTileSamples, n_samples - s_base);
-    uint8_t* out_col = out + 2 * (h0 + hl0);
+    const uint32_t* u_col = s_u + b * kUPitch;
+    const int shift = 16 * half;
+    uint8_t* p = out + 2 * (h0 + hl0) + (s_base + c0) * out_s_samp;
+    const int64_t p_step = 16 * out_s_samp;
 
+    if (kOutVec == 16 && n_my_haps == 8 && rows == kTileSamples) {
+        // full tile, full group: two rows (32*L + c0 and 32*L + 16 + c0) per iteration
 #pragma unroll 4
-    for (int it = 0; it < kTileSamples / (2 * kWarps); ++it) {
-        const int sl = it * (2 * kWarps) + warp * 2 + rsub;
+        for (int L = 0; L < 32; ++L) {
+            const int t = (c0 + L) & 31;
+            const uint32_t w0 = u_col[32 * L + t], w1 = u_col[32 * L + (t ^ 16)];
+            st_stream_v4(p, expand16((w0 >> shift) & 0xffffu));
+            st_stream_v4(p + p_step, expand16((w1 >> shift) & 0xffffu));
+            p += 2 * p_step;
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int it = 0; it < kTileSamples / 16; ++it, p += p_step) {
+        const int sl = it * 16 + c0;
         if (sl >= rows) break;  // rows only grow with `it`
-        const int L = sl >> 5, j = sl & 31;
-        const uint32_t w = s_u[b * kUPitch + 32 * L + ((j + L) & 31)];
-        const uint32_t bits = half ? (w >> 16) : (w & 0xffffu);
-        uint8_t* p = out_col + (s_base + sl) * out_s_samp;
+        const int L = it >> 1, j = ((it & 1) << 4) + c0;
+        const uint32_t bits = (u_col[32 * L + ((j + L) & 31)] >> shift) & 0xffffu;
         if (kOutVec == 16 && n_my_haps == 8) {
-            uint4 o;
-            o.x = spread4(bits & 15u);
-            o.y = spread4((bits >> 4) & 15u);
-            o.z = spread4((bits >> 8) & 15u);
-            o.w = spread4(bits >> 12);
-            st_stream_v4(p, o);
+            st_stream_v4(p, expand16(bits));
         } else if (kOutVec >= 2) {
             for (int q = 0; q < n_my_haps; ++q) {
                 const uint32_t two = (bits >> (2 * q)) & 3u;
@@ -179,7 +321,7 @@ transform_bits_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, in
     if (h >= n_haps) return;
     const uint2* tile_rec =
         reinterpret_cast<const uint2*>(planes) + ((size_t)tile * (size_t)n_keys) * kTileWords + lane;
-    uint2 r = and_keys<false>(tile_rec, hap_key, __ldg(hap_off + h), __ldg(hap_off + h + 1));
+    uint2 r = and_keys_global(tile_rec, hap_key, __ldg(hap_off + h), __ldg(hap_off + h + 1));
     // samples beyond n_samples read as 0, like the planes
     const int64_t rem = n_samples - tile * kTileSamples - 32 * (int64_t)lane;
     const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
@@ -213,6 +355,10 @@ static int check_common(const uint32_t* planes, int64_t n_samples, int64_t n_key
     if (n_keys > 0 && !hap_key) return bad_arg("hap_key is NULL");
     if (n_keys > 0 && (reinterpret_cast<uintptr_t>(planes) & 15))
         return bad_arg("planes must be 16-byte aligned");
+    if (n_keys > (int64_t)kKeyMask) {
+        set_error("too many keys (%lld > 2^30 - 1)", (long long)n_keys);
+        return HT_ERR_UNSUPPORTED;
+    }
     return HT_OK;
 }
 
