@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from haptools_b200 import engine, synth, _cuda
 from haptools_b200.plan import plan_from_refs
 dev = torch.device('cuda')

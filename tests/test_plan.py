@@ -1,0 +1,138 @@
+"""Host planner: mirrors the reference's key dict / index arrays and its exceptions
+(haptools/data/haplotypes.py:1375-1401, haptools/transform.py:103-135)."""
+import types
+
+import numpy as np
+import pytest
+
+import _cases
+from haptools_b200 import data, synth
+from haptools_b200 import transform as htransform
+from haptools_b200.plan import plan_from_haplotypes, plan_from_refs
+from oracle import transform_oracle as orc
+
+NS = types.SimpleNamespace(
+    Variant=data.Variant, Haplotype=data.Haplotype, Haplotypes=data.Haplotypes,
+    GenotypesVCF=data.GenotypesVCF, HaplotypeAncestry=htransform.HaplotypeAncestry,
+    HaplotypesAncestry=htransform.HaplotypesAncestry, GenotypesAncestry=htransform.GenotypesAncestry,
+)
+
+
+def _objects(name):
+    case = _cases.load_case(_cases.GOLDEN_DIR / name)
+    return case, *_cases.build_objects(case, NS)
+
+
+def _check_plan(plan):
+    assert np.all(np.diff(plan.var_col.astype(np.int64)) > 0)
+    assert plan.var_key_off[0] == 0 and plan.var_key_off[-1] == plan.n_keys
+    assert np.all(np.diff(plan.var_key_off.astype(np.int64)) >= 1)
+    assert plan.hap_off[0] == 0 and plan.hap_off[-1] == plan.n_refs
+    assert plan.n_refs == 0 or plan.hap_key.max() < plan.n_keys
+    cv = plan.col_var()
+    assert np.array_equal(np.nonzero(cv >= 0)[0], plan.var_col)
+
+
+@pytest.mark.parametrize("path", _cases.list_golden(), ids=lambda p: p.stem)
+def test_plan_matches_reference_key_dict(path):
+    case, haps, gts = _objects(path.name)
+    hap_list = list(haps.data.values())
+    anc = case["kind"] == "ancestry"
+    plan = plan_from_haplotypes(hap_list, gts, ancestry=anc)
+    _check_plan(plan)
+    alleles, idxs = orc.build_keys(hap_list)
+    assert plan.n_haps == len(hap_list)
+    assert [int(x) for x in np.diff(plan.hap_off.astype(np.int64))] == [len(i) for i in idxs]
+    # same (column, allele) per haplotype-variant reference, whatever the key numbering
+    var_idx = {v: i for i, v in enumerate(gts.variants["id"])}
+    key_col = plan.key_col()
+    flat = plan.hap_key
+    pos = 0
+    for hap in hap_list:
+        for v in hap.variants:
+            k = flat[pos]
+            assert key_col[k] == var_idx[v.id]
+            want = int(v.allele != gts.variants["alleles"][var_idx[v.id]][0]) if anc else \
+                list(gts.variants["alleles"][var_idx[v.id]]).index(v.allele)
+            if gts.data.dtype == np.bool_:
+                want = min(want, 1)
+            assert plan.key_allele[k] == want
+            if anc:
+                assert plan.key_label[k] == gts.ancestry_labels[hap.ancestry]
+            pos += 1
+    if not anc:
+        assert plan.n_keys == len(alleles)  # one key per distinct (variant, allele)
+
+
+def test_missing_allele_raises_like_the_reference():
+    case, haps, gts = _objects("g1_plain_refalt.npz")
+    hap = list(haps.data.values())[0]
+    hap.variants = (data.Variant(start=10114, end=10115, id="1:10114:T:C", allele="G"),)
+    with pytest.raises(ValueError, match="Some alleles were not present in the genotypes"):
+        plan_from_haplotypes(list(haps.data.values()), gts)
+
+
+def test_absent_variant_raises():
+    case, haps, gts = _objects("g1_plain_refalt.npz")
+    hap = list(haps.data.values())[0]
+    hap.variants = hap.variants + (data.Variant(start=5, end=6, id="1:5:A:C", allele="A"),)
+    with pytest.raises(ValueError, match="absent in the provided genotypes"):
+        plan_from_haplotypes([hap], gts, who=f"haplotype '{hap.id}'")
+
+
+def test_duplicate_variant_ids_raise():
+    case, haps, gts = _objects("g1_plain_refalt.npz")
+    gts.variants["id"][1] = gts.variants["id"][0]
+    gts._var_idx = None
+    with pytest.raises(ValueError, match="Found duplicate variant IDs"):
+        plan_from_haplotypes(list(haps.data.values()), gts)
+
+
+def test_unknown_population():
+    case, haps, gts = _objects("g5_ancestry.npz")
+    hap_list = list(haps.data.values())
+    hap_list[0].ancestry = "NOPE"
+    # plural form: uint8 <- -1 (haptools/transform.py:115) overflows on numpy >= 2
+    with pytest.raises(OverflowError):
+        plan_from_haplotypes(hap_list, gts, ancestry=True)
+    plan, never = plan_from_haplotypes(hap_list[:1], gts, ancestry=True, unknown_label="never")
+    assert never.tolist() == [True]
+
+
+def test_type_ids_and_repeats_are_skipped():
+    case, haps, gts = _objects("g1_plain_refalt.npz")
+    haps.data["STR_1"] = data.Repeat(chrom="1", start=1, end=5, id="STR_1")
+    haps.index(force=True)
+    assert haps.type_ids["R"] == ["STR_1"] and len(haps.type_ids["H"]) == 3
+    haps.data["H9"] = data.Haplotype(chrom="1", start=1, end=2, id="H9")
+    haps.index()  # a no-op once built (haptools/data/haplotypes.py:983-985)
+    assert "H9" not in haps.type_ids["H"]
+
+
+def test_plan_from_refs_dedups_and_validates():
+    plan = plan_from_refs(np.array([5, 2, 5, 2]), np.array([1, 0, 1, 1]), np.array([0, 2, 4]), 8)
+    _check_plan(plan)
+    assert plan.n_keys == 3 and plan.n_vars == 2
+    assert plan.var_col.tolist() == [2, 5]
+    assert plan.hap_key.tolist() == [2, 0, 2, 1]
+    with pytest.raises(ValueError):
+        plan_from_refs(np.array([9]), np.array([0]), np.array([0, 1]), 8)
+    with pytest.raises(ValueError):
+        plan_from_refs(np.array([1]), np.array([0]), np.array([0, 2]), 8)
+
+
+def test_synth_numpy_properties():
+    a = synth.synth_gt(50, 200, seed=3, mode=1)
+    b = synth.synth_gt(20, 200, seed=3, mode=1, sample_offset=30)
+    assert np.array_equal(a[30:], b)  # a pure function of the global sample index
+    c = synth.synth_gt(50, 200, seed=3, mode=1, variants=np.arange(100, 200))
+    assert np.array_equal(a[:, 100:], c)
+    assert set(np.unique(a)) <= {0, 1}
+    m = synth.synth_gt(300, 300, seed=3, mode=0, missing_per_64k=2000)
+    assert 0.01 < (m == 255).mean() < 0.06
+    anc = synth.synth_ancestry(10, 5000, seed=1, n_pops=5, tract_len=500)
+    assert anc.max() < 5 and (np.diff(anc[:, :, 0].astype(int), axis=1) != 0).mean() < 0.01
+    plan = synth.synth_plan(5000, 300, seed=1)
+    _check_plan(plan)
+    k = np.diff(plan.hap_off.astype(np.int64))
+    assert k.min() >= 2 and k.max() <= 20
