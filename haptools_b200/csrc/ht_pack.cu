@@ -109,13 +109,14 @@ struct LoadU8 {
 
 struct LoadI32 {
     // pgenlib allele codes (PgenReader.read_alleles_list): int32 matrix (rows, 2*n), element
-    // 2*s + c of row `col`; a.gv = row pitch in BYTES.  -9 (any value outside 0..253) =
-    // missing, stored by the reference as uint8 255 (haptools/data/genotypes.py:1388-1394).
+    // 2*s + c of row `col`; a.gv = row pitch in BYTES.  The reference turns -9 (missing) into -1
+    // and stores the int32 into its uint8 matrix (haptools/data/genotypes.py:1388-1401), i.e.
+    // -9 -> 255 and every other value modulo 256.
     template <bool kAnc>
     static __device__ __forceinline__ uint32_t load(const PackArgs& a, uint32_t col, int64_t s) {
         const int2 v = __ldg(reinterpret_cast<const int2*>(a.gt + (int64_t)col * a.gv) + s);
-        const uint32_t b0 = ((uint32_t)v.x > 253u) ? 255u : (uint32_t)v.x;
-        const uint32_t b1 = ((uint32_t)v.y > 253u) ? 255u : (uint32_t)v.y;
+        const uint32_t b0 = v.x == -9 ? 255u : ((uint32_t)v.x & 0xffu);
+        const uint32_t b1 = v.y == -9 ? 255u : ((uint32_t)v.y & 0xffu);
         return b0 | (b1 << 8);
     }
 };
@@ -296,12 +297,16 @@ __device__ __forceinline__ void store_sector(uint2* rec4, const uint32_t* stage,
     dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// staging words per thread: plain = 4 words x {value[4], invalid[4]}; ancestry = 4 words x
+// {alt[4], label bit 0..2 [4] each, invalid[4]}
+constexpr int kSmStagePlain = 32, kSmStageAnc = 80;
+
 template <bool kAnc>
-__global__ void __launch_bounds__(kPackThreads, 4)
+__global__ void __launch_bounds__(kPackThreads, kAnc ? 2 : 4)
 pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
     // thread-private staging (column = thread): keeps the per-word loop rolled, i.e. the code
     // small enough for the instruction cache
-    __shared__ uint32_t s_stage[32 * kPackThreads];  // 32 KB
+    extern __shared__ uint32_t s_stage[];  // (kAnc ? 80 : 32) * kPackThreads words
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_cblocks;
     const int64_t col0 =
@@ -313,6 +318,7 @@ pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t ti
     uint32_t kb[2] = {0u, 0u}, nk[2] = {0u, 0u};
     int k_ref[2] = {-1, -1}, k_alt[2] = {-1, -1};  // key of allele 0 / 1 (single-pass path)
     bool simple = !kAnc;
+    bool simple_anc = kAnc;  // every key: allele <= 1 and label < 8 -> single-pass ancestry path
     uint32_t refmask = 0u, rounds = 0u;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -332,6 +338,10 @@ pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t ti
                         else simple = false;
                     }
                     simple = simple && nk[i] <= 2;
+                } else {
+                    for (uint32_t k = 0; k < nk[i]; ++k)
+                        simple_anc = simple_anc && __ldg(a.key_allele + kb[i] + k) <= 1 &&
+                                     __ldg(a.key_label + kb[i] + k) < 8;
                 }
             }
         }
@@ -351,7 +361,108 @@ pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t ti
 #pragma unroll
         for (int k = 0; k < 4; ++k) vm[k] = valid_mask(a.n, tile, 4 * grp + k);
 
-        if (simple) {
+        if (kAnc && simple_anc) {
+            // Single pass for (allele, label) keys: accumulate the allele-1 plane and the three
+            // low bit-planes of the label bytes, plus an "invalid" plane (GT byte >= 2 or label
+            // byte >= 8) for 8-row blocks that contain such a byte.  Any key's plane is then
+            // alt^ma & L0^m0 & L1^m1 & L2^m2 & ~invalid.
+            const bool full = (s_grp + 128 <= a.n) && ncols == kSmLaneCols;
+            const uint8_t* p = g + s_grp * a.gs;
+            const uint8_t* pl = l + s_grp * a.as;
+#pragma unroll 1
+            for (int w4 = 0; w4 < 4; ++w4) {
+                uint32_t GA[4], G0[4], G1[4], G2[4], GZ[4];
+                bool any_dirty = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t x[8], c[8];
+                    if (full) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr, p += a.gs, pl += a.as) {
+                            x[rr] = __ldg(reinterpret_cast<const uint32_t*>(p));
+                            c[rr] = __ldg(reinterpret_cast<const uint32_t*>(pl));
+                        }
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr, p += a.gs, pl += a.as) {
+                            x[rr] = c[rr] = 0u;
+                            if (s_grp + 32 * w4 + 8 * q + rr < a.n) {
+                                x[rr] = load_cols4(p, ncols);
+                                c[rr] = load_cols4(pl, ncols);
+                            }
+                        }
+                    }
+                    uint32_t aA = 0u, a0 = 0u, a1 = 0u, a2 = 0u, d = 0u;
+#pragma unroll
+                    for (int rr = 7; rr >= 0; --rr) {  // row rr ends at bit rr of its byte
+                        aA = (aA << 1) + (x[rr] & 0x01010101u);
+                        a0 = (a0 << 1) + (c[rr] & 0x01010101u);
+                        a1 = (a1 << 1) + ((c[rr] >> 1) & 0x01010101u);
+                        a2 = (a2 << 1) + ((c[rr] >> 2) & 0x01010101u);
+                        d |= (x[rr] & 0xfefefefeu) | (c[rr] & 0xf8f8f8f8u);
+                    }
+                    GA[q] = aA;
+                    G0[q] = a0;
+                    G1[q] = a1;
+                    G2[q] = a2;
+                    GZ[q] = 0u;
+                    if (d) {
+                        any_dirty = true;
+                        uint32_t z = 0u;
+#pragma unroll
+                        for (int rr = 7; rr >= 0; --rr) {
+                            const uint32_t y = (x[rr] & 0xfefefefeu) | (c[rr] & 0xf8f8f8f8u);
+                            z = (z << 1) + (nz_bytes_msb(y) >> 7);
+                        }
+                        GZ[q] = z;
+                        if (a.flags) {
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) fl |= qc_flags4(x[rr] & refmask);
+                        }
+                    }
+                }
+                uint32_t w[4], z[4] = {0u, 0u, 0u, 0u};
+                uint32_t* st = stage + (w4 * 20) * kPackThreads;
+                byte_transpose4(GA, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[k * kPackThreads] = w[k];
+                byte_transpose4(G0, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[(4 + k) * kPackThreads] = w[k];
+                byte_transpose4(G1, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[(8 + k) * kPackThreads] = w[k];
+                byte_transpose4(G2, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[(12 + k) * kPackThreads] = w[k];
+                if (any_dirty) byte_transpose4(GZ, z);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st[(16 + k) * kPackThreads] = z[k];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll 1
+                for (uint32_t r = 0; r < nk[i]; ++r) {
+                    const uint32_t al = __ldg(a.key_allele + kb[i] + r), lb = __ldg(a.key_label + kb[i] + r);
+                    const uint32_t mA = al ? 0u : 0xffffffffu, m0 = (lb & 1u) ? 0u : 0xffffffffu;
+                    const uint32_t m1 = (lb & 2u) ? 0u : 0xffffffffu, m2 = (lb & 4u) ? 0u : 0xffffffffu;
+                    uint32_t o[8];
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const uint32_t* st = stage + (w4 * 20 + 2 * i + c) * kPackThreads;
+                            const uint32_t v = (st[0] ^ mA) & (st[4 * kPackThreads] ^ m0) &
+                                               (st[8 * kPackThreads] ^ m1) & (st[12 * kPackThreads] ^ m2);
+                            o[2 * w4 + c] = v & ~st[16 * kPackThreads] & vm[w4];
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(record(a, tile, kb[i] + r) + 4 * grp);
+                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        } else if (simple) {
             // all 128 rows exist and both of my columns do: no per-row checks, and the 32 row
             // loads of a word are issued back to back (32 independent loads in flight)
             const bool full = (s_grp + 128 <= a.n) && ncols == kSmLaneCols;
@@ -476,7 +587,7 @@ static bool aligned(const void* p, int64_t stride, int to) {
 // (PackArgs, uint32 n_xblocks, [int64 extra,] int64 tile0).
 template <class K>
 static int launch_tiled(K kernel, const PackArgs& a, int64_t n_xblocks, int64_t extra,
-                        bool has_extra, cudaStream_t st) {
+                        bool has_extra, cudaStream_t st, size_t smem = 0) {
     const int64_t n_tiles = ht_num_tiles(a.n);
     if (n_xblocks <= 0 || n_tiles <= 0) return HT_OK;
     if (n_xblocks > 0x7fffffff) {
@@ -484,6 +595,8 @@ static int launch_tiled(K kernel, const PackArgs& a, int64_t n_xblocks, int64_t 
         return HT_ERR_UNSUPPORTED;
     }
     uint32_t nxb = (uint32_t)n_xblocks;
+    if (smem > 48 * 1024)
+        HT_CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // a grid holds at most 2^31-1 blocks: launch ranges of tiles
     const int64_t tiles_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_xblocks);
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
@@ -491,7 +604,7 @@ static int launch_tiled(K kernel, const PackArgs& a, int64_t n_xblocks, int64_t 
         void* args_extra[] = {(void*)&a, (void*)&nxb, (void*)&extra, (void*)&t0};
         void* args_plain[] = {(void*)&a, (void*)&nxb, (void*)&t0};
         HT_CUDA_TRY(cudaLaunchKernel((const void*)kernel, dim3((unsigned)(nt * n_xblocks)),
-                                     dim3(kPackThreads), has_extra ? args_extra : args_plain, 0, st));
+                                     dim3(kPackThreads), has_extra ? args_extra : args_plain, smem, st));
     }
     return HT_OK;
 }
@@ -558,8 +671,10 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                 return HT_ERR_UNSUPPORTED;
             }
             const int64_t n_cblocks = (n_cols + kSmCtaCols - 1) / kSmCtaCols;
-            return anc ? launch_tiled(pack_sm_kernel<true>, a, n_cblocks, 0, true, st)
-                       : launch_tiled(pack_sm_kernel<false>, a, n_cblocks, 0, true, st);
+            return anc ? launch_tiled(pack_sm_kernel<true>, a, n_cblocks, 0, true, st,
+                                      sizeof(uint32_t) * kSmStageAnc * kPackThreads)
+                       : launch_tiled(pack_sm_kernel<false>, a, n_cblocks, 0, true, st,
+                                      sizeof(uint32_t) * kSmStagePlain * kPackThreads);
         }
         default:
             return bad_arg("unknown pack mode");

@@ -1,0 +1,141 @@
+"""
+Streamed PGEN input (BASELINE.json configs[4]).
+
+The reference materialises the whole `(n, p, 3)` uint8 matrix on the host before transforming
+(`GenotypesPLINK.read`, haptools/data/genotypes.py:1298-1406: pgenlib fills `(chunk, 2n)` int32
+buffers that are cast and transposed chunk by chunk).  Here those same int32 chunk buffers are
+the unit of work: the reader fills page-locked ring buffers, each chunk is DMA'd on a copy
+stream while the next one is being read, and `ht_pack_i32` turns it straight into bit-planes
+-- `gts.data` is never built.  Only the variants some haplotype references are read (as
+`transform_haps` already asks for, haptools/transform.py:602-620).  One transform launch
+follows once all planes exist.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import _cuda, engine
+from ._cuda import check
+from .plan import TransformPlan
+
+
+class ArrayPgenReader:
+    """
+    Stand-in for `pgenlib.PgenReader` with its buffer contract (pgenlib is not installed in
+    this image): `read_alleles_list(variant_idxs uint32[c], allele_int32_out int32[c, 2n])`,
+    allele codes 0/1/2..., -9 = missing.  Backed by a `(p, 2n)` int32 array or by a callable
+    `fill(variant_idxs, out)`.
+    """
+
+    def __init__(self, alleles=None, n_samples: int = None, fill=None):
+        self._alleles, self._fill = alleles, fill
+        self._n = n_samples if n_samples is not None else alleles.shape[1] // 2
+
+    def get_raw_sample_ct(self) -> int:
+        return self._n
+
+    def read_alleles_list(self, variant_idxs, allele_int32_out, hap_maj: bool = False):
+        if hap_maj:
+            raise NotImplementedError("haplotype-major mode is not part of the contract used")
+        if self._fill is not None:
+            self._fill(variant_idxs, allele_int32_out)
+        else:
+            np.take(self._alleles, variant_idxs, axis=0, out=allele_int32_out)
+
+
+def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan: TransformPlan,
+                          chunk_variants: int = 1024, device=None, n_host_buffers: int = 3,
+                          fmt: str = "u8", to_host: bool = True, stats: dict = None):
+    """
+    reader        object with pgenlib's `read_alleles_list(idx, int32[c, 2n])`
+    variant_idxs  uint32 indices (into the PGEN) of the variants to read; column j of the plan
+                  is variant_idxs[j] (so plan.n_cols == len(variant_idxs))
+    Returns the `(n, H, 2)` bool result (numpy if `to_host`, else a device uint8 tensor), or the
+    packed result with fmt="bits".  `stats` (optional dict) receives timings and byte counts.
+    """
+    engine.require_cuda()
+    variant_idxs = np.ascontiguousarray(variant_idxs, dtype=np.uint32)
+    p = len(variant_idxs)
+    if p != plan.n_cols:
+        raise ValueError(f"plan was made for {plan.n_cols} variant columns, {p} variants are to be read")
+    if plan.has_ancestry:
+        raise ValueError("local ancestry is not part of the PGEN stream")
+    n, H = int(n_samples), plan.n_haps
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = _cuda.lib()
+    t_start = time.perf_counter()
+    with torch.cuda.device(dev):
+        dplan = engine.DevicePlan(plan, dev)
+        planes = engine.alloc_planes(n, plan.n_keys, dev)
+        # only referenced columns are read: chunk over plan.var_col
+        cols = plan.var_col.astype(np.int64)
+        V = len(cols)
+        chunk = max(1, min(int(chunk_variants), max(V, 1)))
+        row_in_chunk = torch.from_numpy((np.arange(V, dtype=np.int64) % chunk).astype(np.int32)).to(dev)
+        host = [engine.pinned_empty((chunk, 2 * n), np.int32) for _ in range(min(n_host_buffers, max(1, -(-V // chunk))))]
+        devbuf = [torch.empty((chunk, 2 * n), dtype=torch.int32, device=dev) for _ in range(2)]
+        s_in, s_cmp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        s_in.wait_stream(cur)
+        s_cmp.wait_stream(cur)
+        ev_h2d = [None] * len(host)   # host buffer may be refilled once its copy has left
+        ev_pack = [None] * 2          # device buffer may be overwritten once it has been packed
+        t_read = 0.0
+        h2d_bytes = 0
+        for k, v0 in enumerate(range(0, V, chunk)):
+            v1 = min(V, v0 + chunk)
+            c = v1 - v0
+            hb, db = k % len(host), k % 2
+            if ev_h2d[hb] is not None:
+                ev_h2d[hb].synchronize()
+            t0 = time.perf_counter()
+            reader.read_alleles_list(variant_idxs[cols[v0:v1]], host[hb][:c])
+            t_read += time.perf_counter() - t0
+            if ev_pack[db] is not None:
+                s_in.wait_event(ev_pack[db])
+            nbytes = c * 2 * n * 4
+            check(lib.ht_copy2d(devbuf[db].data_ptr(), nbytes, host[hb].ctypes.data, nbytes, nbytes, 1,
+                                _cuda.HT_COPY_H2D, s_in.cuda_stream), "ht_copy2d")
+            h2d_bytes += nbytes
+            ev_h2d[hb] = s_in.record_event()
+            s_cmp.wait_event(ev_h2d[hb])
+            check(
+                lib.ht_pack_i32(devbuf[db].data_ptr(), 2 * n, n, row_in_chunk.data_ptr() + 4 * v0,
+                                dplan.var_key_off.data_ptr() + 4 * v0, dplan.key_allele.data_ptr(), c, 0,
+                                plan.n_keys, planes.data_ptr(), 0, s_cmp.cuda_stream),
+                "ht_pack_i32",
+            )
+            ev_pack[db] = s_cmp.record_event()
+        t_packed = time.perf_counter()
+        with torch.cuda.stream(s_cmp):
+            if fmt == "bits":
+                tiles = (n + engine.TILE - 1) // engine.TILE
+                res = torch.empty((tiles, H, 32, 2), dtype=torch.int32, device=dev)
+                engine.transform_bits(dplan, planes, n, res, s_cmp)
+            else:
+                pitch = engine.out_pitch(H)
+                buf = torch.empty((n, pitch), dtype=torch.uint8, device=dev)
+                engine.transform_u8(dplan, planes, n, buf.data_ptr(), pitch, s_cmp)
+                res = buf[:, : 2 * H].unflatten(1, (H, 2))
+        s_cmp.synchronize()
+        cur.wait_stream(s_cmp)
+        t_done = time.perf_counter()
+        if to_host:
+            if fmt == "bits":
+                res = res.cpu().numpy().view(np.uint32)
+            else:
+                host_out = np.empty((n, H, 2), dtype=np.uint8)
+                rows = max(1, (256 << 20) // max(2 * H, 1))
+                for s0 in range(0, n, rows):
+                    m = min(rows, n - s0)
+                    check(lib.ht_copy2d(host_out.ctypes.data + s0 * 2 * H, 2 * H, buf.data_ptr() + s0 * pitch, pitch,
+                                        2 * H, m, _cuda.HT_COPY_D2H, cur.cuda_stream), "ht_copy2d")
+                cur.synchronize()
+                res = host_out.view(np.bool_)
+        if stats is not None:
+            stats.update(read_s=t_read, stream_s=t_packed - t_start, total_device_s=t_done - t_start,
+                         total_s=time.perf_counter() - t_start, h2d_bytes=h2d_bytes, chunks=-(-V // chunk) if V else 0)
+    return res

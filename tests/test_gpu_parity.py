@@ -13,7 +13,7 @@ from oracle import transform_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-from haptools_b200 import _cuda, data, engine, synth  # noqa: E402
+from haptools_b200 import _cuda, data, engine, stream, synth  # noqa: E402
 from haptools_b200 import transform as htransform  # noqa: E402
 from haptools_b200.plan import plan_from_haplotypes, plan_from_refs  # noqa: E402
 
@@ -203,6 +203,30 @@ def test_random_ancestry_vs_oracle(n, p, H, mode):
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
 
 
+@pytest.mark.parametrize("case", ["labels_ge_8_in_keys", "labels_ge_8_in_data_only"])
+def test_ancestry_label_ranges_sample_major(case):
+    """The single-pass ancestry pack handles labels < 8; bigger labels in the DATA must never
+    match (invalid plane), bigger labels in the KEYS fall back to the per-key pass."""
+    rng = np.random.default_rng(77)
+    n, p, H = 1500, 40, 60
+    gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=12, missing=0.02)
+    if case == "labels_ge_8_in_data_only":
+        # same data, haplotype populations restricted to 0..7
+        k = np.diff(plan.hap_off.astype(np.int64))
+        ref_col = plan.key_col().astype(np.int64)[plan.hap_key]
+        ref_allele = plan.key_allele[plan.hap_key].astype(np.int64)
+        hap_label = rng.integers(0, 8, size=H)
+        plan = plan_from_refs(ref_col, ref_allele, plan.hap_off.astype(np.int64), p, np.repeat(hap_label, k))
+        idxs = [np.arange(plan.hap_off[h], plan.hap_off[h + 1]) for h in range(H)]
+        want = orc.transform_core(gt[:, ref_col], ref_allele.astype(np.uint8), idxs, anc[:, ref_col], hap_label.astype(np.uint8))
+        assert plan.key_label.max() < 8 and anc.max() >= 8
+    else:
+        assert plan.key_label.max() >= 8
+    for mode, lay in (("sm", "C"), ("vm", "F"), ("generic", "C3")):
+        out, _ = _run_device(_layouts(gt)[lay], plan, _layouts(anc)[lay], mode)
+        np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=mode)
+
+
 def test_long_haplotype_unstaged_keys():
     """A haplotype block whose key list exceeds the shared-memory stage (3072 keys)."""
     rng = np.random.default_rng(5)
@@ -293,6 +317,27 @@ def test_pack_i32_chunks():
     engine.transform_u8(dplan, planes, n, out.data_ptr(), out.stride(0))
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out[:, : 2 * H].cpu().numpy().reshape(n, H, 2).view(np.bool_), want)
+
+
+@pytest.mark.parametrize("chunk", [7, 64, 1000])
+def test_pgen_stream(chunk):
+    """pgenlib-style int32 chunk buffers -> planes, never building gts.data (config 5 / N1)."""
+    rng = np.random.default_rng(21)
+    n, p_file, H = 1300, 400, 90
+    read = np.sort(rng.choice(p_file, size=150, replace=False)).astype(np.uint32)  # variants the .hap needs
+    gt, _, plan, want = _random_arrays(rng, n, len(read), H, multi=True, missing=0.04)
+    file_alleles = rng.integers(0, 2, size=(p_file, 2 * n), dtype=np.int32)
+    as_i32 = gt.transpose(1, 0, 2).reshape(len(read), 2 * n).astype(np.int32)
+    as_i32[as_i32 == 255] = -9  # pgenlib's missing code; 254 stays 254, as in the reference's cast
+    file_alleles[read] = as_i32
+    reader = stream.ArrayPgenReader(file_alleles)
+    stats = {}
+    got = stream.transform_pgen_stream(reader, read, n, plan, chunk_variants=chunk, stats=stats)
+    np.testing.assert_array_equal(got, want)
+    assert stats["h2d_bytes"] == plan.n_vars * 2 * n * 4  # only referenced variants travel
+    bits = stream.transform_pgen_stream(reader, read, n, plan, chunk_variants=chunk, fmt="bits")
+    from haptools_b200 import dist as hdist
+    np.testing.assert_array_equal(hdist.unpack_result_bits(bits, n), want)
 
 
 # ------------------------------------------------------------------ host pipeline
