@@ -8,17 +8,33 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libhaptools_cuda.so"
-ABI_VERSION = 4
+import os
+
+# HT_LIB_PATH lets experiments (profiles/) load an alternative build of the same ABI
+LIB_PATH = Path(os.environ.get("HT_LIB_PATH") or Path(__file__).resolve().parent / "libhaptools_cuda.so")
+ABI_VERSION = 5
 
 HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
 HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
 HT_PACK_AUTO, HT_PACK_GENERIC, HT_PACK_VARIANT_MAJOR, HT_PACK_SAMPLE_MAJOR = 0, 1, 2, 3
+HT_PACK_SAMPLE_MAJOR_BIALLELIC = 4
 HT_COPY_H2D, HT_COPY_D2H, HT_COPY_D2D = 1, 2, 3
 TILE_SAMPLES = 1024
 RECORD_BYTES = 256
 
 _p, _i64, _i32, _u32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
+
+
+
+class PackTables(C.Structure):
+    """struct ht_pack_tables (include/haptools_cuda.h); pointers are device addresses."""
+
+    _fields_ = [
+        ("n_cols", _i64), ("n_vars", _i64), ("n_keys", _i64),
+        ("var_col", _p), ("var_key_off", _p), ("key_allele", _p), ("key_label", _p),
+        ("col_var", _p), ("col_key01", _p), ("var_other", _p), ("n_var_other", _i64),
+    ]
+
 
 # name -> (restype, argtypes); every symbol include/haptools_cuda.h declares
 SIGNATURES = {
@@ -26,10 +42,7 @@ SIGNATURES = {
     "ht_last_error": (C.c_char_p, []),
     "ht_num_tiles": (_i64, [_i64]),
     "ht_plane_bytes": (_sz, [_i64, _i64]),
-    "ht_pack_u8": (
-        _i32,
-        [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _i32, _p],
-    ),
+    "ht_pack_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p]),
     "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),

@@ -39,7 +39,9 @@ struct PackArgs {
     const uint32_t* var_key_off;
     const uint8_t* key_allele;
     const uint8_t* key_label;
-    const int32_t* col_var;  // dense column -> variant map (sample-major kernel)
+    const int32_t* col_var;  // dense column -> variant map (sample-major kernels)
+    const int32_t* col_key01;  // dense column -> {key of allele 0, key of allele 1} (-1 = none)
+    const uint32_t* var_sel;   // optional indirection: generic kernel packs variants var_sel[i]
     int64_t n_cols;
     int64_t n_vars;
     int64_t n_keys;     // record pitch of the plane workspace (total keys)
@@ -126,8 +128,9 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_generic_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_vblocks;
-    const int64_t v = (int64_t)(blockIdx.x % n_vblocks) * kPackWarps + warp;
+    int64_t v = (int64_t)(blockIdx.x % n_vblocks) * kPackWarps + warp;
     if (v >= a.n_vars) return;
+    if (a.var_sel) v = __ldg(a.var_sel + v);
     const uint32_t col = __ldg(a.var_col + v);
     const uint32_t kb = __ldg(a.var_key_off + v), ke = __ldg(a.var_key_off + v + 1);
     const int64_t s0 = tile * kTileSamples + lane;
@@ -293,6 +296,9 @@ __device__ __forceinline__ void store_sector(uint2* rec4, const uint32_t* stage,
         }
     }
     uint4* dst = reinterpret_cast<uint4*>(rec4);
+#ifdef HT_EXP_NO_PLANE_STORE  // experiment only (profiles/): keep the math alive, drop the stores
+    if ((o[0] ^ o[1] ^ o[2] ^ o[3] ^ o[4] ^ o[5] ^ o[6] ^ o[7]) != 0x9e3779b9u) return;
+#endif
     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
     dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
@@ -579,6 +585,162 @@ pack_sm_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t ti
     publish_flags(a.flags, fl);
 }
 
+// -----------------------------------------------------------------------------------------
+// sample-major kernel, biallelic fast path (s_strand == 1, s_var == 2, 16-byte aligned rows)
+//   CTA  = (tile of 1024 samples) x (64 consecutive columns); 8 warps = 2 row halves x 4
+//          column chunks of 16 columns
+//   warp = 16 words (512 rows) x 16 columns
+//   lane = (word wl = lane / 2, sub-chunk = lane % 2): 8 columns = 16 bytes of each of the 32
+//          rows of ONE word -- two lanes make a full 32-byte sector of every row
+// The lane folds its 32 rows into byte-wide shift registers and byte-transposes (as above);
+// it then owns word `wl` of 8 columns x 2 strands, so the lanes with the same sub-chunk hold
+// 16 consecutive words of a key: every store instruction writes 2 x 128 contiguous bytes of
+// plane records and no shared-memory staging is needed.  (A profile of the previous mapping
+// showed its scattered 16-byte stores doubling the kernel time although planes are 20 % of
+// the bytes.)  Only keys "allele 0" / "allele 1" are handled (dense table col_key01 from the
+// planner); variants with other keys go through the generic kernel (var_sel).
+// Missing / multi-allelic bytes (>= 2) are exact: a lane that saw one re-reads its rows and
+// builds the invalid plane.
+// -----------------------------------------------------------------------------------------
+constexpr int kSm2CtaCols = 64;
+
+__device__ __forceinline__ uint4 load_row16(const uint8_t* p, int ncols) {
+    if (ncols >= 8) return __ldg(reinterpret_cast<const uint4*>(p));
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // word j = my columns 2j, 2j+1 (2 bytes each; rows are 2-byte aligned)
+        w[j] = 0u;
+        if (2 * j < ncols) w[j] = *reinterpret_cast<const uint16_t*>(p + 4 * j);
+        if (2 * j + 1 < ncols) w[j] |= (uint32_t)*reinterpret_cast<const uint16_t*>(p + 4 * j + 2) << 16;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// byte k of `src` (k = 0..3) replaces byte q of each of dst[0..3]
+__device__ __forceinline__ void insert_bytes(uint32_t (&dst)[4], uint32_t src, int q) {
+    // PRMT selector: identity 0x3210 with nibble q replaced by 4 + k (bytes 4..7 = src)
+    const uint32_t keep = 0x3210u & ~(0xfu << (4 * q));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = prmt(dst[k], src, keep | ((4u + k) << (4 * q)));
+}
+
+__global__ void __launch_bounds__(kPackThreads, 3)
+pack_sm2_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_cblocks;
+    const int word = (warp >> 2) * 16 + (lane >> 1);
+    const int64_t col0 = (cblock0 + blockIdx.x % n_cblocks) * kSm2CtaCols + (warp & 3) * 16 + (lane & 1) * 8;
+    const int ncols = (int)min((int64_t)8, a.n_cols - col0);  // may be <= 0
+    if (ncols <= 0) return;
+    const int64_t s0 = tile * kTileSamples + 32 * word;
+    const int nrows = (int)min((int64_t)32, a.n - s0);  // <= 0: the word lies beyond the samples
+
+    // keys of my 8 columns: {allele 0, allele 1}, -1 = no such key
+    int2 kk[8];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        kk[i] = make_int2(-1, -1);
+        if (i < ncols) kk[i] = __ldg(reinterpret_cast<const int2*>(a.col_key01) + col0 + i);
+        any = any || kk[i].x >= 0 || kk[i].y >= 0;
+    }
+    if (!any) return;
+
+    const uint8_t* base = a.gt + s0 * a.gs + col0 * 2;
+    const bool full = nrows == 32 && ncols == 8;
+    // W[j][k]: word of byte column 4*j + k = my column 2*j + k/2, strand k & 1
+    uint32_t W[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) W[j][k] = 0u;
+    uint32_t d = 0u;
+    {
+        const uint8_t* p = base;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {  // 8-row blocks; 8 independent 16-byte loads in flight
+            uint4 x[8];
+            if (full) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) {
+                    x[rr] = make_uint4(0u, 0u, 0u, 0u);
+                    if (8 * q + rr < nrows) x[rr] = load_row16(p, ncols);
+                }
+            }
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {  // row rr ends at bit rr of its byte
+                a0 = (a0 << 1) + (x[rr].x & 0x01010101u);
+                a1 = (a1 << 1) + (x[rr].y & 0x01010101u);
+                a2 = (a2 << 1) + (x[rr].z & 0x01010101u);
+                a3 = (a3 << 1) + (x[rr].w & 0x01010101u);
+                d |= (x[rr].x | x[rr].y) | (x[rr].z | x[rr].w);
+            }
+            insert_bytes(W[0], a0, q);
+            insert_bytes(W[1], a1, q);
+            insert_bytes(W[2], a2, q);
+            insert_bytes(W[3], a3, q);
+        }
+    }
+    const uint32_t vm = valid_mask(a.n, tile, word);
+    if (!(d & 0xfefefefeu)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t w0 = W[i >> 1][2 * (i & 1)], w1 = W[i >> 1][2 * (i & 1) + 1];
+            if (kk[i].y >= 0) record(a, tile, (uint32_t)kk[i].y)[word] = make_uint2(w0 & vm, w1 & vm);
+            if (kk[i].x >= 0) record(a, tile, (uint32_t)kk[i].x)[word] = make_uint2(~w0 & vm, ~w1 & vm);
+        }
+        return;
+    }
+    // some byte >= 2 (missing or multi-allelic call): build the invalid plane from a second
+    // read of my rows (L1/L2 hits), one row at a time
+    uint32_t Z[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Z[j][k] = 0u;
+    uint32_t fl = 0u;
+    uint32_t refmask[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        refmask[j] = ((kk[2 * j].x >= 0 || kk[2 * j].y >= 0) ? 0x0000ffffu : 0u) |
+                     ((kk[2 * j + 1].x >= 0 || kk[2 * j + 1].y >= 0) ? 0xffff0000u : 0u);
+    const uint8_t* p = base;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        uint32_t z0 = 0u, z1 = 0u, z2 = 0u, z3 = 0u;
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr, p += a.gs) {  // row rr enters at bit 7, ends at bit rr
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (8 * q + rr < nrows) x = load_row16(p, ncols);
+            z0 = (z0 >> 1) | nz_bytes_msb(x.x & 0xfefefefeu);
+            z1 = (z1 >> 1) | nz_bytes_msb(x.y & 0xfefefefeu);
+            z2 = (z2 >> 1) | nz_bytes_msb(x.z & 0xfefefefeu);
+            z3 = (z3 >> 1) | nz_bytes_msb(x.w & 0xfefefefeu);
+            if (a.flags)
+                fl |= qc_flags4(x.x & refmask[0]) | qc_flags4(x.y & refmask[1]) |
+                      qc_flags4(x.z & refmask[2]) | qc_flags4(x.w & refmask[3]);
+        }
+        insert_bytes(Z[0], z0, q);
+        insert_bytes(Z[1], z1, q);
+        insert_bytes(Z[2], z2, q);
+        insert_bytes(Z[3], z3, q);
+    }
+    if (a.flags && fl) {
+        if (fl & ~*reinterpret_cast<volatile uint32_t*>(a.flags)) atomicOr(a.flags, fl);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t w0 = W[i >> 1][2 * (i & 1)], w1 = W[i >> 1][2 * (i & 1) + 1];
+        const uint32_t ok0 = ~Z[i >> 1][2 * (i & 1)] & vm, ok1 = ~Z[i >> 1][2 * (i & 1) + 1] & vm;
+        if (kk[i].y >= 0) record(a, tile, (uint32_t)kk[i].y)[word] = make_uint2(w0 & ok0, w1 & ok1);
+        if (kk[i].x >= 0) record(a, tile, (uint32_t)kk[i].x)[word] = make_uint2(~w0 & ok0, ~w1 & ok1);
+    }
+}
+
 static bool aligned(const void* p, int64_t stride, int to) {
     return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)stride) & (uintptr_t)(to - 1)) == 0;
 }
@@ -627,33 +789,39 @@ extern "C" {
 
 int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t gt_s_strand,
                const uint8_t* anc, int64_t anc_s_samp, int64_t anc_s_var, int64_t anc_s_strand,
-               int64_t n_samples, const uint32_t* var_col, const uint32_t* var_key_off,
-               const uint8_t* key_allele, const uint8_t* key_label, int64_t n_vars,
-               int64_t n_keys, const int32_t* col_var, int64_t n_cols, uint32_t* planes,
-               uint32_t* flags, int mode, void* stream) {
+               int64_t n_samples, const ht_pack_tables* t, uint32_t* planes, uint32_t* flags,
+               int mode, void* stream) {
     using namespace ht;
+    if (!t) return bad_arg("tables is NULL");
     PackArgs a;
     a.gt = gt; a.gs = gt_s_samp; a.gv = gt_s_var; a.gc = gt_s_strand;
     a.anc = anc; a.as = anc_s_samp; a.av = anc_s_var; a.ac = anc_s_strand;
     a.n = n_samples;
-    a.var_col = var_col; a.var_key_off = var_key_off;
-    a.key_allele = key_allele; a.key_label = key_label;
-    a.col_var = col_var; a.n_cols = n_cols;
-    a.n_vars = n_vars; a.n_keys = n_keys; a.key_base = 0;
+    a.var_col = t->var_col; a.var_key_off = t->var_key_off;
+    a.key_allele = t->key_allele; a.key_label = t->key_label;
+    a.col_var = t->col_var; a.col_key01 = t->col_key01; a.var_sel = nullptr;
+    a.n_cols = t->n_cols;
+    a.n_vars = t->n_vars; a.n_keys = t->n_keys; a.key_base = 0;
     a.planes = planes; a.flags = flags;
     if (int rc = check_pack(a)) return rc;
-    if (n_vars == 0 || n_samples == 0) return HT_OK;
+    if (a.n_vars == 0 || n_samples == 0) return HT_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_cols = t->n_cols;
 
     const bool vm_ok = gt_s_strand == 1 && gt_s_samp == 2 && aligned(gt, gt_s_var, 16) &&
                        (!anc || (anc_s_strand == 1 && anc_s_samp == 2 && aligned(anc, anc_s_var, 16)));
-    const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 4) && col_var &&
+    const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 4) && t->col_var &&
                        n_cols > 0 &&
                        (!anc || (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 4)));
+    const bool sm2_ok = !anc && gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 16) &&
+                        t->col_key01 && aligned(t->col_key01, 0, 8) && n_cols > 0 &&
+                        t->n_var_other >= 0 && (t->n_var_other == 0 || t->var_other);
     if (mode == HT_PACK_AUTO)
-        mode = vm_ok ? HT_PACK_VARIANT_MAJOR : (sm_ok ? HT_PACK_SAMPLE_MAJOR : HT_PACK_GENERIC);
+        mode = vm_ok ? HT_PACK_VARIANT_MAJOR
+                     : (sm2_ok ? HT_PACK_SAMPLE_MAJOR_BIALLELIC
+                               : (sm_ok ? HT_PACK_SAMPLE_MAJOR : HT_PACK_GENERIC));
 
-    const int64_t n_vblocks = (n_vars + kPackWarps - 1) / kPackWarps;
+    const int64_t n_vblocks = (a.n_vars + kPackWarps - 1) / kPackWarps;
     switch (mode) {
         case HT_PACK_GENERIC:
             return anc ? launch_tiled(pack_generic_kernel<LoadU8, true>, a, n_vblocks, 0, false, st)
@@ -676,6 +844,23 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                        : launch_tiled(pack_sm_kernel<false>, a, n_cblocks, 0, true, st,
                                       sizeof(uint32_t) * kSmStagePlain * kPackThreads);
         }
+        case HT_PACK_SAMPLE_MAJOR_BIALLELIC: {
+            if (!sm2_ok) {
+                set_error("biallelic sample-major pack needs s_strand=1, s_var=2, 16-byte aligned rows, "
+                          "no ancestry, col_key01 and var_other");
+                return HT_ERR_UNSUPPORTED;
+            }
+            const int64_t n_cblocks = (n_cols + kSm2CtaCols - 1) / kSm2CtaCols;
+            if (int rc = launch_tiled(pack_sm2_kernel, a, n_cblocks, 0, true, st)) return rc;
+            if (t->n_var_other > 0) {  // the few variants with other keys: generic kernel
+                PackArgs o = a;
+                o.var_sel = t->var_other;
+                o.n_vars = t->n_var_other;
+                return launch_tiled(pack_generic_kernel<LoadU8, false>, o,
+                                    (o.n_vars + kPackWarps - 1) / kPackWarps, 0, false, st);
+            }
+            return HT_OK;
+        }
         default:
             return bad_arg("unknown pack mode");
     }
@@ -693,7 +878,7 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
     a.n = n_samples;
     a.var_col = var_col; a.var_key_off = var_key_off;
     a.key_allele = key_allele; a.key_label = nullptr;
-    a.col_var = nullptr; a.n_cols = 0;
+    a.col_var = nullptr; a.col_key01 = nullptr; a.var_sel = nullptr; a.n_cols = 0;
     a.n_vars = n_vars; a.n_keys = n_keys_total; a.key_base = key_base;
     a.planes = planes; a.flags = flags;
     if (int rc = check_pack(a)) return rc;

@@ -16,6 +16,8 @@ Two entry points:
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -61,6 +63,14 @@ class DevicePlan:
         self.hap_off = up(plan.hap_off, np.int32)
         self.hap_key = up(plan.hap_key, np.int32)
         self.col_var = up(plan.col_var(), np.int32)
+        col_key01, var_other = plan.biallelic_tables()
+        self.col_key01 = up(col_key01, np.int32)
+        self.var_other = up(var_other, np.int32)
+        self.tables = _cuda.PackTables(
+            plan.n_cols, plan.n_vars, plan.n_keys, _ptr(self.var_col), _ptr(self.var_key_off),
+            _ptr(self.key_allele), _ptr(self.key_label), _ptr(self.col_var), _ptr(self.col_key01),
+            _ptr(self.var_other) if len(var_other) else None, len(var_other),
+        )
 
     n_haps = property(lambda self: self.plan.n_haps)
     n_keys = property(lambda self: self.plan.n_keys)
@@ -90,9 +100,7 @@ def pack(dplan: DevicePlan, gt_ptr: int, gt_strides, n_samples: int, planes: tor
     check(
         _cuda.lib().ht_pack_u8(
             gt_ptr, *map(int, gt_strides), anc_ptr, *map(int, anc_strides), n_samples,
-            _ptr(dplan.var_col), _ptr(dplan.var_key_off), _ptr(dplan.key_allele), _ptr(dplan.key_label),
-            dplan.n_vars, dplan.n_keys, _ptr(dplan.col_var), dplan.plan.n_cols,
-            _ptr(planes), _ptr(flags), mode, _stream_ptr(stream),
+            ctypes.byref(dplan.tables), _ptr(planes), _ptr(flags), mode, _stream_ptr(stream),
         ),
         "ht_pack_u8",
     )

@@ -64,6 +64,25 @@ class TransformPlan:
         out[self.var_col] = np.arange(self.n_vars, dtype=np.int32)
         return out
 
+    def biallelic_tables(self):
+        """
+        (col_key01, var_other) for the biallelic sample-major pack kernel: col_key01 is
+        (n_cols, 2) int32 = {key of allele 0, key of allele 1} of every column (-1 = none) for
+        the variants whose keys are all plain alleles 0/1; var_other lists the remaining
+        variants (multi-allelic keys; every variant when the plan carries ancestry labels).
+        """
+        out = np.full((self.n_cols, 2), -1, dtype=np.int32)
+        if self.has_ancestry:
+            return out, np.arange(self.n_vars, dtype=np.uint32)
+        off = self.var_key_off.astype(np.int64)
+        key_var = np.repeat(np.arange(self.n_vars), np.diff(off))
+        simple_var = np.ones(self.n_vars, dtype=bool)
+        simple_var[key_var[self.key_allele > 1]] = False
+        ok = simple_var[key_var]
+        cols = self.var_col.astype(np.int64)[key_var[ok]]
+        out[cols, self.key_allele[ok].astype(np.int64)] = np.nonzero(ok)[0].astype(np.int32)
+        return out, np.nonzero(~simple_var)[0].astype(np.uint32)
+
     def key_col(self) -> np.ndarray:
         """Column of each key, (A,) uint32."""
         return np.repeat(self.var_col, np.diff(self.var_key_off.astype(np.int64)))

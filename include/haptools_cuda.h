@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define HT_ABI_VERSION 4
+#define HT_ABI_VERSION 5
 
 #define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
 #define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
@@ -70,6 +70,12 @@ extern "C" {
 #define HT_PACK_SAMPLE_MAJOR 3  /* variants contiguous along a sample row (PGEN reader
                                    layout, genotypes.py:1346-1352): 128-bit loads +
                                    bytewise bit accumulation down the sample rows     */
+#define HT_PACK_SAMPLE_MAJOR_BIALLELIC 4 /* same layout, 16-byte aligned rows, no ancestry,
+                                   tables->col_key01 given: one pass builds the allele-0 and
+                                   allele-1 planes of every column with 128-byte coalesced
+                                   record stores; variants listed in tables->var_other
+                                   (keys other than plain allele 0/1) go through the generic
+                                   kernel.  What HT_PACK_AUTO picks when it can.            */
 
 /* direction of ht_copy2d */
 #define HT_COPY_H2D 1
@@ -87,6 +93,37 @@ int64_t ht_num_tiles(int64_t n_samples);
 size_t ht_plane_bytes(int64_t n_samples, int64_t n_keys);
 
 /*
+ * Index tables of the pack kernels (all DEVICE pointers; built by the host planner,
+ * haptools_b200/plan.py).
+ *   var_col[V]        column (index along the variant axis of gt/anc) of each distinct
+ *                     referenced variant, ascending.
+ *   var_key_off[V+1]  CSR: keys var_key_off[v] .. var_key_off[v+1]-1 belong to var_col[v].
+ *   key_allele[A]     allele index each key matches against (`alleles.index(allele)`,
+ *                     haplotypes.py:1395; `int(allele != REF)`, transform.py:130).
+ *   key_label[A]      ancestry label of each key (NULL iff no ancestry array is packed).
+ *   col_var[n_cols]   optional dense inverse of var_col (-1 = column not referenced); needed
+ *                     by HT_PACK_SAMPLE_MAJOR (it walks whole rows of gt).
+ *   col_key01[2*n_cols]  optional: {key of allele 0, key of allele 1} of each column, -1 =
+ *                     no such key; (-1, -1) for unreferenced columns and for the columns of
+ *                     the variants in var_other.  Needed by HT_PACK_SAMPLE_MAJOR_BIALLELIC.
+ *   var_other[n_var_other]  indices (into var_col) of the variants that have a key other than
+ *                     plain allele 0 / allele 1 (multi-allelic index, ancestry label).
+ */
+typedef struct ht_pack_tables {
+    int64_t n_cols;
+    int64_t n_vars;
+    int64_t n_keys;
+    const uint32_t* var_col;
+    const uint32_t* var_key_off;
+    const uint8_t* key_allele;
+    const uint8_t* key_label;
+    const int32_t* col_var;
+    const int32_t* col_key01;
+    const uint32_t* var_other;
+    int64_t n_var_other;
+} ht_pack_tables;
+
+/*
  * K1 -- pack.  Replaces the column gather `gts.subset(variants=...)`
  * (haplotypes.py:1388 -> genotypes.py:440) and `np.equal(allele_arr, gts.data[:, :, :2])`
  * (haplotypes.py:1404; transform.py:137) and, when `anc` is given,
@@ -95,16 +132,7 @@ size_t ht_plane_bytes(int64_t n_samples, int64_t n_keys);
  *   gt            genotype bytes (uint8 or numpy bool), element (s, v, c) at
  *                 gt + s*gt_s_samp + v*gt_s_var + c*gt_s_strand, c in {0,1}; never copied.
  *   anc           local-ancestry label bytes with its own strides, or NULL.
- *   var_col[V]    column (index along the variant axis of gt/anc) of each distinct
- *                 referenced variant.
- *   var_key_off[V+1]  CSR: keys var_key_off[v] .. var_key_off[v+1]-1 belong to var_col[v].
- *   key_allele[A] allele index each key matches against (`alleles.index(allele)`,
- *                 haplotypes.py:1395; `int(allele != REF)`, transform.py:130).
- *   key_label[A]  ancestry label of each key (NULL iff anc is NULL).
- *   col_var[n_cols]  optional (may be NULL) dense inverse of var_col: index into var_col of
- *                 each column of gt, or -1 for columns no haplotype references.  Needed
- *                 by the sample-major kernel only (it walks whole rows of gt); without it
- *                 HT_PACK_AUTO falls back to the generic kernel for that layout.
+ *   tables        see ht_pack_tables (the struct itself is HOST memory).
  *   planes        workspace of ht_plane_bytes(n_samples, A) bytes, 16-byte aligned;
  *                 fully overwritten.
  *   flags         optional (may be NULL) uint32 that the kernel ORs HT_FLAG_* bits into.
@@ -112,11 +140,8 @@ size_t ht_plane_bytes(int64_t n_samples, int64_t n_keys);
  */
 int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t gt_s_strand,
                const uint8_t* anc, int64_t anc_s_samp, int64_t anc_s_var,
-               int64_t anc_s_strand, int64_t n_samples, const uint32_t* var_col,
-               const uint32_t* var_key_off, const uint8_t* key_allele,
-               const uint8_t* key_label, int64_t n_vars, int64_t n_keys,
-               const int32_t* col_var, int64_t n_cols, uint32_t* planes, uint32_t* flags,
-               int mode, void* stream);
+               int64_t anc_s_strand, int64_t n_samples, const ht_pack_tables* tables,
+               uint32_t* planes, uint32_t* flags, int mode, void* stream);
 
 /*
  * K1 for pgenlib chunk buffers (GenotypesPLINK._iterate, genotypes.py:1373-1402):

@@ -42,6 +42,7 @@ def test_abi_version_matches_header(lib):
 def test_constants_match_header():
     text = HEADER.read_text()
     for name in ("HT_PACK_AUTO", "HT_PACK_GENERIC", "HT_PACK_VARIANT_MAJOR", "HT_PACK_SAMPLE_MAJOR",
+                 "HT_PACK_SAMPLE_MAJOR_BIALLELIC",
                  "HT_COPY_H2D", "HT_COPY_D2H", "HT_COPY_D2D", "HT_ERR_BAD_ARG", "HT_ERR_CUDA", "HT_ERR_UNSUPPORTED"):
         m = re.search(rf"#define {name} (\d+)", text)
         assert m and int(m.group(1)) == getattr(_cuda, name), name
@@ -61,7 +62,10 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert rc == _cuda.HT_ERR_BAD_ARG and b"negative" in lib.ht_last_error()
     with pytest.raises(ValueError):
         _cuda.check(rc, "ht_transform_u8")
-    rc = lib.ht_pack_u8(None, 0, 0, 0, None, 0, 0, 0, 5, None, None, None, None, 3, 3, None, 0, None, None, 0, None)
+    rc = lib.ht_pack_u8(None, 0, 0, 0, None, 0, 0, 0, 5, None, None, None, 0, None)
+    assert rc == _cuda.HT_ERR_BAD_ARG and b"tables" in lib.ht_last_error()
+    tables = _cuda.PackTables(8, 3, 3, None, None, None, None, None, None, None, 0)
+    rc = lib.ht_pack_u8(None, 0, 0, 0, None, 0, 0, 0, 5, ctypes.byref(tables), None, None, 0, None)
     assert rc == _cuda.HT_ERR_BAD_ARG
     rc = lib.ht_copy2d(None, 0, None, 0, 4, 4, 1, None)
     assert rc == _cuda.HT_ERR_BAD_ARG

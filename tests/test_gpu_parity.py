@@ -24,7 +24,7 @@ NS = types.SimpleNamespace(
 )
 GOLDEN = _cases.list_golden()
 MODES = {"generic": _cuda.HT_PACK_GENERIC, "vm": _cuda.HT_PACK_VARIANT_MAJOR, "sm": _cuda.HT_PACK_SAMPLE_MAJOR,
-         "auto": _cuda.HT_PACK_AUTO}
+         "sm2": _cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC, "auto": _cuda.HT_PACK_AUTO}
 
 
 # ------------------------------------------------------------------ class-level API
@@ -104,7 +104,9 @@ def _eligible(mode, lay, n, p):
     if mode == "vm":
         return lay == "F" and n % 8 == 0
     if mode == "sm":
-        return lay == "C" and p % 4 == 0
+        return lay == "C" and p % 2 == 0
+    if mode == "sm2":
+        return lay == "C" and p % 8 == 0
     return True
 
 
@@ -114,12 +116,14 @@ def _case_plan(case):
     return plan_from_haplotypes(list(haps.data.values()), gts, ancestry=anc)
 
 
-@pytest.mark.parametrize("mode", ["generic", "vm", "sm", "auto"])
+@pytest.mark.parametrize("mode", ["generic", "vm", "sm", "sm2", "auto"])
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.stem)
 def test_golden_every_kernel(path, mode):
     case = _cases.load_case(path)
     if case["kind"] == "ancestry" and case["gt"].shape[2] != 2:
         pytest.skip("reference rejects a phase column in the ancestry path")
+    if case["kind"] == "ancestry" and mode == "sm2":
+        pytest.skip("the biallelic kernel does not take ancestry")
     plan = _case_plan(case)
     ran = 0
     for lay, gt in _layouts(case["gt"]).items():
@@ -164,16 +168,33 @@ def _random_arrays(rng, n, p, H, max_k=6, multi=False, missing=0.0, n_pops=0, lo
 
 SHAPES = [
     (1, 4, 1), (31, 8, 7), (32, 12, 8), (33, 16, 9), (1023, 20, 127), (1024, 24, 128), (1025, 28, 129),
-    (2504, 64, 300), (4096, 132, 16), (3000, 260, 257),
+    (2504, 64, 300), (4096, 132, 16), (3000, 260, 257), (2100, 136, 64), (5000, 72, 40),
 ]
 
 
-@pytest.mark.parametrize("mode", ["generic", "vm", "sm"])
+def test_biallelic_sample_major_clean_and_padded_rows():
+    """The fast kernel on clean biallelic data (no invalid plane), on a row pitch larger than
+    2p (device copies of host arrays are pitched), and with an odd column count."""
+    rng = np.random.default_rng(9)
+    for n, p, H in ((3000, 77, 50), (1100, 250, 30)):
+        gt, _, plan, want = _random_arrays(rng, n, p, H, multi=False, missing=0.0)
+        pitch = (2 * p + 15) // 16 * 16 + 32
+        buf = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, : 2 * p] = torch.from_numpy(gt.reshape(n, 2 * p)).cuda()
+        view = torch.as_strided(buf, (n, p, 2), (pitch, 2, 1))
+        dplan = engine.DevicePlan(plan)
+        for mode in ("sm2", "sm", "auto"):
+            out = engine.transform_device(view, dplan, pack_mode=MODES[mode])
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=mode)
+
+
+@pytest.mark.parametrize("mode", ["generic", "vm", "sm", "sm2"])
 @pytest.mark.parametrize("n,p,H", SHAPES)
 def test_random_vs_oracle(n, p, H, mode):
     rng = np.random.default_rng(n * 7919 + p * 31 + H)
     gt, _, plan, want = _random_arrays(rng, n, p, H, multi=True, missing=0.03)
-    lay = {"generic": "C3", "vm": "F", "sm": "C"}[mode]
+    lay = {"generic": "C3", "vm": "F", "sm": "C", "sm2": "C"}[mode]
     if not _eligible(mode, lay, n, p):
         # pad the sample axis in memory so that variant rows are 16-byte aligned
         if mode == "vm":
@@ -208,7 +229,7 @@ def test_ancestry_label_ranges_sample_major(case):
     """The single-pass ancestry pack handles labels < 8; bigger labels in the DATA must never
     match (invalid plane), bigger labels in the KEYS fall back to the per-key pass."""
     rng = np.random.default_rng(77)
-    n, p, H = 1500, 40, 60
+    n, p, H = 1504, 40, 60
     gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=12, missing=0.02)
     if case == "labels_ge_8_in_data_only":
         # same data, haplotype populations restricted to 0..7

@@ -109,6 +109,19 @@ def test_type_ids_and_repeats_are_skipped():
     assert "H9" not in haps.type_ids["H"]
 
 
+def test_biallelic_tables():
+    # column 2: alleles 0 and 1; column 5: allele 1 only; column 6: allele 2 (-> var_other)
+    plan = plan_from_refs(np.array([2, 2, 5, 6, 6]), np.array([0, 1, 1, 2, 0]), np.array([0, 2, 5]), 8)
+    ck, other = plan.biallelic_tables()
+    assert ck.shape == (8, 2) and ck.dtype == np.int32
+    assert ck[2].tolist() == [0, 1] and ck[5].tolist() == [-1, 2] and ck[6].tolist() == [-1, -1]
+    assert (ck[[0, 1, 3, 4, 7]] == -1).all()
+    assert other.tolist() == [2] and plan.var_col[other[0]] == 6
+    anc = plan_from_refs(np.array([2]), np.array([1]), np.array([0, 1]), 8, np.array([3]))
+    ck, other = anc.biallelic_tables()
+    assert (ck == -1).all() and other.tolist() == [0]
+
+
 def test_plan_from_refs_dedups_and_validates():
     plan = plan_from_refs(np.array([5, 2, 5, 2]), np.array([1, 0, 1, 1]), np.array([0, 2, 4]), 8)
     _check_plan(plan)
