@@ -32,7 +32,7 @@ class PackTables(C.Structure):
     _fields_ = [
         ("n_cols", _i64), ("n_vars", _i64), ("n_keys", _i64),
         ("var_col", _p), ("var_key_off", _p), ("key_allele", _p), ("key_label", _p),
-        ("col_var", _p), ("col_key01", _p), ("var_other", _p), ("n_var_other", _i64),
+        ("col_var", _p), ("col_key01", _p), ("col_key_range", _p), ("var_other", _p), ("n_var_other", _i64),
     ]
 
 

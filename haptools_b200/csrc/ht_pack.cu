@@ -41,6 +41,7 @@ struct PackArgs {
     const uint8_t* key_label;
     const int32_t* col_var;  // dense column -> variant map (sample-major kernels)
     const int32_t* col_key01;  // dense column -> {key of allele 0, key of allele 1} (-1 = none)
+    const int32_t* col_key_range;  // dense column -> {first key, key count} (ancestry fast path)
     const uint32_t* var_sel;   // optional indirection: generic kernel packs variants var_sel[i]
     int64_t n_cols;
     int64_t n_vars;
@@ -741,6 +742,230 @@ pack_sm2_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t t
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// sample-major kernel with local ancestry, same mapping as pack_sm2_kernel (lane = one word x
+// 8 columns; 128-byte coalesced record stores).  One pass over the genotype rows builds the
+// allele-1 plane, one pass over the ancestry rows the three low bit-planes of the label bytes
+// (their 8-row block accumulators are parked in thread-private shared memory); every key
+// (allele a <= 1, label l < 8) is then  alt^ma & L0^m0 & L1^m1 & L2^m2 & ~invalid,  where the
+// invalid plane (GT byte >= 2 or label byte >= 8) is only built by lanes that saw such a byte.
+// The keys of a warp's 16 columns are a contiguous range: their {first key, count} pairs and
+// (allele, label) bytes are staged once per warp.  Variants with other keys -> generic kernel.
+// -----------------------------------------------------------------------------------------
+constexpr int kAncKeyStage = 128;  // staged (allele, label) pairs per warp
+constexpr size_t kSm2AncSmem = sizeof(uint32_t) * 48 * kPackThreads + sizeof(int2) * kPackWarps * 16 +
+                               sizeof(uint16_t) * kPackWarps * kAncKeyStage;
+
+__global__ void __launch_bounds__(kPackThreads, 2)
+pack_sm2_anc_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* gl = s_dyn + threadIdx.x;  // [(q * 3 + bit) * 4 + j][thread]
+    int2* s_kr = reinterpret_cast<int2*>(s_dyn + 48 * kPackThreads);
+    uint16_t* s_ki = reinterpret_cast<uint16_t*>(s_kr + kPackWarps * 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_cblocks;
+    const int word = (warp >> 2) * 16 + (lane >> 1);
+    const int64_t wcol0 = (cblock0 + blockIdx.x % n_cblocks) * kSm2CtaCols + (warp & 3) * 16;
+    if (wcol0 >= a.n_cols) return;  // warp-uniform
+    const int64_t col0 = wcol0 + (lane & 1) * 8;
+    const int ncols = (int)max((int64_t)0, min((int64_t)8, a.n_cols - col0));
+    const int64_t s0 = tile * kTileSamples + 32 * word;
+    const int nrows = (int)max((int64_t)0, min((int64_t)32, a.n - s0));
+    const bool have_rows = ncols > 0 && nrows > 0;
+    const bool full = nrows == 32 && ncols == 8;
+    int2* my_kr = s_kr + warp * 16;
+    uint16_t* my_ki = s_ki + warp * kAncKeyStage;
+
+    // (1) key ranges of the warp's 16 columns (lanes 0..15 fetch one each)
+    int2 kr = make_int2(0, 0);
+    if (lane < 16 && wcol0 + lane < a.n_cols) kr = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + lane);
+
+    // (2) genotype rows -> allele-1 plane words W[j][k] (byte column 4j + k)
+    uint32_t W[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) W[j][k] = 0u;
+    uint32_t d = 0u;
+    const uint8_t* gbase = a.gt + s0 * a.gs + col0 * 2;
+    const uint8_t* lbase = a.anc + s0 * a.as + col0 * 2;
+    if (have_rows) {
+        const uint8_t* p = gbase;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint4 x[8];
+            if (full) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) {
+                    x[rr] = make_uint4(0u, 0u, 0u, 0u);
+                    if (8 * q + rr < nrows) x[rr] = load_row16(p, ncols);
+                }
+            }
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {
+                a0 = (a0 << 1) + (x[rr].x & 0x01010101u);
+                a1 = (a1 << 1) + (x[rr].y & 0x01010101u);
+                a2 = (a2 << 1) + (x[rr].z & 0x01010101u);
+                a3 = (a3 << 1) + (x[rr].w & 0x01010101u);
+                d |= ((x[rr].x | x[rr].y) | (x[rr].z | x[rr].w)) & 0xfefefefeu;
+            }
+            insert_bytes(W[0], a0, q);
+            insert_bytes(W[1], a1, q);
+            insert_bytes(W[2], a2, q);
+            insert_bytes(W[3], a3, q);
+        }
+    }
+
+    // (3) publish the key ranges, find the warp's key span, fetch its (allele, label) bytes
+    if (lane < 16) my_kr[lane] = kr;
+    int kmin = kr.y > 0 ? kr.x : 0x7fffffff, kmax = kr.y > 0 ? kr.x + kr.y : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (kmax <= kmin) return;  // none of the warp's columns is referenced (warp-uniform)
+    const int n_k = kmax - kmin;
+    const bool ki_staged = n_k <= kAncKeyStage;
+    uint32_t ki_reg[kAncKeyStage / 32];
+#pragma unroll
+    for (int t = 0; t < kAncKeyStage / 32; ++t) {
+        const int idx = lane + 32 * t;
+        ki_reg[t] = 0u;
+        if (ki_staged && idx < n_k)
+            ki_reg[t] = (uint32_t)__ldg(a.key_allele + kmin + idx) | ((uint32_t)__ldg(a.key_label + kmin + idx) << 8);
+    }
+
+    // (4) ancestry rows -> block accumulators of label bits 0..2, parked in shared memory
+    if (have_rows) {
+        const uint8_t* p = lbase;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint4 c[8];
+            if (full) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.as) c[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.as) {
+                    c[rr] = make_uint4(0u, 0u, 0u, 0u);
+                    if (8 * q + rr < nrows) c[rr] = load_row16(p, ncols);
+                }
+            }
+#pragma unroll
+            for (int bit = 0; bit < 3; ++bit) {
+                uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+                for (int rr = 7; rr >= 0; --rr) {
+                    a0 = (a0 << 1) + ((c[rr].x >> bit) & 0x01010101u);
+                    a1 = (a1 << 1) + ((c[rr].y >> bit) & 0x01010101u);
+                    a2 = (a2 << 1) + ((c[rr].z >> bit) & 0x01010101u);
+                    a3 = (a3 << 1) + ((c[rr].w >> bit) & 0x01010101u);
+                }
+                uint32_t* dst = gl + ((q * 3 + bit) * 4) * kPackThreads;
+                dst[0] = a0;
+                dst[kPackThreads] = a1;
+                dst[2 * kPackThreads] = a2;
+                dst[3 * kPackThreads] = a3;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) d |= ((c[rr].x | c[rr].y) | (c[rr].z | c[rr].w)) & 0xf8f8f8f8u;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 48; ++i) gl[i * kPackThreads] = 0u;
+    }
+
+    // (5) publish the key bytes
+    if (ki_staged) {
+#pragma unroll
+        for (int t = 0; t < kAncKeyStage / 32; ++t)
+            if (lane + 32 * t < n_k) my_ki[lane + 32 * t] = (uint16_t)ki_reg[t];
+    }
+    __syncwarp();
+
+    // (6) invalid plane, only for lanes that saw a GT byte >= 2 or a label byte >= 8
+    uint32_t Z[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Z[j][k] = 0u;
+    if (d) {
+        uint32_t fl = 0u, refmask[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c_lo = (lane & 1) * 8 + 2 * j;
+            refmask[j] = (my_kr[c_lo].y > 0 ? 0x0000ffffu : 0u) | (my_kr[c_lo + 1].y > 0 ? 0xffff0000u : 0u);
+        }
+        const uint8_t* pg = gbase;
+        const uint8_t* pl = lbase;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint32_t z0 = 0u, z1 = 0u, z2 = 0u, z3 = 0u;
+#pragma unroll 1
+            for (int rr = 0; rr < 8; ++rr, pg += a.gs, pl += a.as) {
+                uint4 x = make_uint4(0u, 0u, 0u, 0u), c = make_uint4(0u, 0u, 0u, 0u);
+                if (8 * q + rr < nrows) {
+                    x = load_row16(pg, ncols);
+                    c = load_row16(pl, ncols);
+                }
+                z0 = (z0 >> 1) | nz_bytes_msb((x.x & 0xfefefefeu) | (c.x & 0xf8f8f8f8u));
+                z1 = (z1 >> 1) | nz_bytes_msb((x.y & 0xfefefefeu) | (c.y & 0xf8f8f8f8u));
+                z2 = (z2 >> 1) | nz_bytes_msb((x.z & 0xfefefefeu) | (c.z & 0xf8f8f8f8u));
+                z3 = (z3 >> 1) | nz_bytes_msb((x.w & 0xfefefefeu) | (c.w & 0xf8f8f8f8u));
+                if (a.flags)
+                    fl |= qc_flags4(x.x & refmask[0]) | qc_flags4(x.y & refmask[1]) |
+                          qc_flags4(x.z & refmask[2]) | qc_flags4(x.w & refmask[3]);
+            }
+            insert_bytes(Z[0], z0, q);
+            insert_bytes(Z[1], z1, q);
+            insert_bytes(Z[2], z2, q);
+            insert_bytes(Z[3], z3, q);
+        }
+        if (a.flags && fl) {
+            if (fl & ~*reinterpret_cast<volatile uint32_t*>(a.flags)) atomicOr(a.flags, fl);
+        }
+    }
+
+    // (7) every key of my 8 columns: combine the planes, store word `word` of both strands
+    if (ncols <= 0) return;
+    const uint32_t vm = valid_mask(a.n, tile, word);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t L[3][4];
+#pragma unroll
+        for (int bit = 0; bit < 3; ++bit) {
+            uint32_t G[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) G[q] = gl[((q * 3 + bit) * 4 + j) * kPackThreads];
+            byte_transpose4(G, L[bit]);
+        }
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+            const int2 r = my_kr[(lane & 1) * 8 + 2 * j + cp];
+#pragma unroll 1
+            for (int t = 0; t < r.y; ++t) {
+                const int key = r.x + t;
+                const uint32_t info = ki_staged ? (uint32_t)my_ki[key - kmin]
+                                                : ((uint32_t)__ldg(a.key_allele + key) | ((uint32_t)__ldg(a.key_label + key) << 8));
+                const uint32_t mA = (info & 1u) ? 0u : 0xffffffffu, m0 = (info & 0x100u) ? 0u : 0xffffffffu;
+                const uint32_t m1 = (info & 0x200u) ? 0u : 0xffffffffu, m2 = (info & 0x400u) ? 0u : 0xffffffffu;
+                uint2 o;
+                o.x = (W[j][2 * cp] ^ mA) & (L[0][2 * cp] ^ m0) & (L[1][2 * cp] ^ m1) & (L[2][2 * cp] ^ m2) &
+                      ~Z[j][2 * cp] & vm;
+                o.y = (W[j][2 * cp + 1] ^ mA) & (L[0][2 * cp + 1] ^ m0) & (L[1][2 * cp + 1] ^ m1) &
+                      (L[2][2 * cp + 1] ^ m2) & ~Z[j][2 * cp + 1] & vm;
+                record(a, tile, (uint32_t)key)[word] = o;
+            }
+        }
+    }
+}
+
 static bool aligned(const void* p, int64_t stride, int to) {
     return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)stride) & (uintptr_t)(to - 1)) == 0;
 }
@@ -799,7 +1024,7 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
     a.n = n_samples;
     a.var_col = t->var_col; a.var_key_off = t->var_key_off;
     a.key_allele = t->key_allele; a.key_label = t->key_label;
-    a.col_var = t->col_var; a.col_key01 = t->col_key01; a.var_sel = nullptr;
+    a.col_var = t->col_var; a.col_key01 = t->col_key01; a.col_key_range = t->col_key_range; a.var_sel = nullptr;
     a.n_cols = t->n_cols;
     a.n_vars = t->n_vars; a.n_keys = t->n_keys; a.key_base = 0;
     a.planes = planes; a.flags = flags;
@@ -813,9 +1038,11 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
     const bool sm_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 4) && t->col_var &&
                        n_cols > 0 &&
                        (!anc || (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 4)));
-    const bool sm2_ok = !anc && gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 16) &&
-                        t->col_key01 && aligned(t->col_key01, 0, 8) && n_cols > 0 &&
-                        t->n_var_other >= 0 && (t->n_var_other == 0 || t->var_other);
+    const bool sm2_ok = gt_s_strand == 1 && gt_s_var == 2 && aligned(gt, gt_s_samp, 16) && n_cols > 0 &&
+                        t->n_var_other >= 0 && (t->n_var_other == 0 || t->var_other) &&
+                        (anc ? (anc_s_strand == 1 && anc_s_var == 2 && aligned(anc, anc_s_samp, 16) &&
+                                t->col_key_range && aligned(t->col_key_range, 0, 8))
+                             : (t->col_key01 && aligned(t->col_key01, 0, 8)));
     if (mode == HT_PACK_AUTO)
         mode = vm_ok ? HT_PACK_VARIANT_MAJOR
                      : (sm2_ok ? HT_PACK_SAMPLE_MAJOR_BIALLELIC
@@ -847,17 +1074,20 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
         case HT_PACK_SAMPLE_MAJOR_BIALLELIC: {
             if (!sm2_ok) {
                 set_error("biallelic sample-major pack needs s_strand=1, s_var=2, 16-byte aligned rows, "
-                          "no ancestry, col_key01 and var_other");
+                          "var_other and col_key01 (col_key_range with ancestry)");
                 return HT_ERR_UNSUPPORTED;
             }
             const int64_t n_cblocks = (n_cols + kSm2CtaCols - 1) / kSm2CtaCols;
-            if (int rc = launch_tiled(pack_sm2_kernel, a, n_cblocks, 0, true, st)) return rc;
+            if (int rc = anc ? launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem)
+                             : launch_tiled(pack_sm2_kernel, a, n_cblocks, 0, true, st))
+                return rc;
             if (t->n_var_other > 0) {  // the few variants with other keys: generic kernel
                 PackArgs o = a;
                 o.var_sel = t->var_other;
                 o.n_vars = t->n_var_other;
-                return launch_tiled(pack_generic_kernel<LoadU8, false>, o,
-                                    (o.n_vars + kPackWarps - 1) / kPackWarps, 0, false, st);
+                const int64_t nvb = (o.n_vars + kPackWarps - 1) / kPackWarps;
+                return anc ? launch_tiled(pack_generic_kernel<LoadU8, true>, o, nvb, 0, false, st)
+                           : launch_tiled(pack_generic_kernel<LoadU8, false>, o, nvb, 0, false, st);
             }
             return HT_OK;
         }
@@ -878,7 +1108,7 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
     a.n = n_samples;
     a.var_col = var_col; a.var_key_off = var_key_off;
     a.key_allele = key_allele; a.key_label = nullptr;
-    a.col_var = nullptr; a.col_key01 = nullptr; a.var_sel = nullptr; a.n_cols = 0;
+    a.col_var = nullptr; a.col_key01 = nullptr; a.col_key_range = nullptr; a.var_sel = nullptr; a.n_cols = 0;
     a.n_vars = n_vars; a.n_keys = n_keys_total; a.key_base = key_base;
     a.planes = planes; a.flags = flags;
     if (int rc = check_pack(a)) return rc;

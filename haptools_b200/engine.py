@@ -63,13 +63,14 @@ class DevicePlan:
         self.hap_off = up(plan.hap_off, np.int32)
         self.hap_key = up(plan.hap_key, np.int32)
         self.col_var = up(plan.col_var(), np.int32)
-        col_key01, var_other = plan.biallelic_tables()
+        col_key01, col_key_range, var_other = plan.fast_tables()
         self.col_key01 = up(col_key01, np.int32)
+        self.col_key_range = up(col_key_range, np.int32)
         self.var_other = up(var_other, np.int32)
         self.tables = _cuda.PackTables(
             plan.n_cols, plan.n_vars, plan.n_keys, _ptr(self.var_col), _ptr(self.var_key_off),
             _ptr(self.key_allele), _ptr(self.key_label), _ptr(self.col_var), _ptr(self.col_key01),
-            _ptr(self.var_other) if len(var_other) else None, len(var_other),
+            _ptr(self.col_key_range), _ptr(self.var_other) if len(var_other) else None, len(var_other),
         )
 
     n_haps = property(lambda self: self.plan.n_haps)

@@ -64,24 +64,42 @@ class TransformPlan:
         out[self.var_col] = np.arange(self.n_vars, dtype=np.int32)
         return out
 
-    def biallelic_tables(self):
+    def fast_tables(self):
         """
-        (col_key01, var_other) for the biallelic sample-major pack kernel: col_key01 is
-        (n_cols, 2) int32 = {key of allele 0, key of allele 1} of every column (-1 = none) for
-        the variants whose keys are all plain alleles 0/1; var_other lists the remaining
-        variants (multi-allelic keys; every variant when the plan carries ancestry labels).
+        Dense per-column tables for the single-pass sample-major pack kernels; returns
+        (col_key01, col_key_range, var_other).
+
+        plain plans     col_key01 (n_cols, 2) int32 = {key of allele 0, key of allele 1} (-1 =
+                        none) for the variants whose keys are all plain alleles 0/1
+        ancestry plans  col_key_range (n_cols, 2) int32 = {first key, key count} for the variants
+                        whose keys all have allele <= 1 and label < 8
+        var_other lists the remaining variants (packed by the generic kernel).
         """
-        out = np.full((self.n_cols, 2), -1, dtype=np.int32)
-        if self.has_ancestry:
-            return out, np.arange(self.n_vars, dtype=np.uint32)
         off = self.var_key_off.astype(np.int64)
         key_var = np.repeat(np.arange(self.n_vars), np.diff(off))
+        bad_key = self.key_allele > 1
+        if self.has_ancestry:
+            bad_key = bad_key | (self.key_label > 7)
         simple_var = np.ones(self.n_vars, dtype=bool)
-        simple_var[key_var[self.key_allele > 1]] = False
+        simple_var[key_var[bad_key]] = False
+        var_other = np.nonzero(~simple_var)[0].astype(np.uint32)
+        cols = self.var_col.astype(np.int64)
+        if self.has_ancestry:
+            rng = np.zeros((self.n_cols, 2), dtype=np.int32)
+            rng[cols[simple_var], 0] = off[:-1][simple_var]
+            rng[cols[simple_var], 1] = np.diff(off)[simple_var]
+            return None, rng, var_other
+        k01 = np.full((self.n_cols, 2), -1, dtype=np.int32)
         ok = simple_var[key_var]
-        cols = self.var_col.astype(np.int64)[key_var[ok]]
-        out[cols, self.key_allele[ok].astype(np.int64)] = np.nonzero(ok)[0].astype(np.int32)
-        return out, np.nonzero(~simple_var)[0].astype(np.uint32)
+        k01[cols[key_var[ok]], self.key_allele[ok].astype(np.int64)] = np.nonzero(ok)[0].astype(np.int32)
+        return k01, None, var_other
+
+    def biallelic_tables(self):
+        """(col_key01, var_other) of a plain plan; see fast_tables."""
+        k01, _, other = self.fast_tables()
+        if k01 is None:
+            return np.full((self.n_cols, 2), -1, dtype=np.int32), np.arange(self.n_vars, dtype=np.uint32)
+        return k01, other
 
     def key_col(self) -> np.ndarray:
         """Column of each key, (A,) uint32."""

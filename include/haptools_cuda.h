@@ -70,12 +70,12 @@ extern "C" {
 #define HT_PACK_SAMPLE_MAJOR 3  /* variants contiguous along a sample row (PGEN reader
                                    layout, genotypes.py:1346-1352): 128-bit loads +
                                    bytewise bit accumulation down the sample rows     */
-#define HT_PACK_SAMPLE_MAJOR_BIALLELIC 4 /* same layout, 16-byte aligned rows, no ancestry,
-                                   tables->col_key01 given: one pass builds the allele-0 and
-                                   allele-1 planes of every column with 128-byte coalesced
-                                   record stores; variants listed in tables->var_other
-                                   (keys other than plain allele 0/1) go through the generic
-                                   kernel.  What HT_PACK_AUTO picks when it can.            */
+#define HT_PACK_SAMPLE_MAJOR_BIALLELIC 4 /* same layout, 16-byte aligned rows, tables->col_key01
+                                   (with ancestry: col_key_range) given: one pass over the rows
+                                   builds the planes of every allele-0/1 key with 128-byte
+                                   coalesced record stores; variants listed in
+                                   tables->var_other go through the generic kernel.  What
+                                   HT_PACK_AUTO picks when it can.                         */
 
 /* direction of ht_copy2d */
 #define HT_COPY_H2D 1
@@ -106,8 +106,11 @@ size_t ht_plane_bytes(int64_t n_samples, int64_t n_keys);
  *   col_key01[2*n_cols]  optional: {key of allele 0, key of allele 1} of each column, -1 =
  *                     no such key; (-1, -1) for unreferenced columns and for the columns of
  *                     the variants in var_other.  Needed by HT_PACK_SAMPLE_MAJOR_BIALLELIC.
- *   var_other[n_var_other]  indices (into var_col) of the variants that have a key other than
- *                     plain allele 0 / allele 1 (multi-allelic index, ancestry label).
+ *   col_key_range[2*n_cols]  optional, ancestry plans: {first key, key count} of each column
+ *                     whose keys all have allele <= 1 and label < 8; {0, 0} otherwise.
+ *   var_other[n_var_other]  indices (into var_col) of the variants NOT covered by col_key01 /
+ *                     col_key_range (multi-allelic index, label >= 8); they are packed by
+ *                     the generic kernel.
  */
 typedef struct ht_pack_tables {
     int64_t n_cols;
@@ -119,6 +122,7 @@ typedef struct ht_pack_tables {
     const uint8_t* key_label;
     const int32_t* col_var;
     const int32_t* col_key01;
+    const int32_t* col_key_range;
     const uint32_t* var_other;
     int64_t n_var_other;
 } ht_pack_tables;

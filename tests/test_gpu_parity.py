@@ -122,8 +122,6 @@ def test_golden_every_kernel(path, mode):
     case = _cases.load_case(path)
     if case["kind"] == "ancestry" and case["gt"].shape[2] != 2:
         pytest.skip("reference rejects a phase column in the ancestry path")
-    if case["kind"] == "ancestry" and mode == "sm2":
-        pytest.skip("the biallelic kernel does not take ancestry")
     plan = _case_plan(case)
     ran = 0
     for lay, gt in _layouts(case["gt"]).items():
@@ -214,12 +212,12 @@ def test_random_vs_oracle(n, p, H, mode):
     assert flags == want_flags
 
 
-@pytest.mark.parametrize("mode", ["generic", "vm", "sm"])
-@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1032, 36, 70), (2504, 64, 200)])
+@pytest.mark.parametrize("mode", ["generic", "vm", "sm", "sm2"])
+@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1032, 40, 70), (2504, 64, 200), (3104, 200, 333)])
 def test_random_ancestry_vs_oracle(n, p, H, mode):
     rng = np.random.default_rng(n + p + H)
-    gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=4, missing=0.01)
-    lay = {"generic": "C3", "vm": "F", "sm": "C"}[mode]
+    gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=4, missing=0.01 if H != 200 else 0.0)
+    lay = {"generic": "C3", "vm": "F", "sm": "C", "sm2": "C"}[mode]
     out, _ = _run_device(_layouts(gt)[lay], plan, _layouts(anc)[lay], mode)
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
 
@@ -243,7 +241,7 @@ def test_ancestry_label_ranges_sample_major(case):
         assert plan.key_label.max() < 8 and anc.max() >= 8
     else:
         assert plan.key_label.max() >= 8
-    for mode, lay in (("sm", "C"), ("vm", "F"), ("generic", "C3")):
+    for mode, lay in (("sm2", "C"), ("sm", "C"), ("vm", "F"), ("generic", "C3")):
         out, _ = _run_device(_layouts(gt)[lay], plan, _layouts(anc)[lay], mode)
         np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=mode)
 

@@ -117,9 +117,13 @@ def test_biallelic_tables():
     assert ck[2].tolist() == [0, 1] and ck[5].tolist() == [-1, 2] and ck[6].tolist() == [-1, -1]
     assert (ck[[0, 1, 3, 4, 7]] == -1).all()
     assert other.tolist() == [2] and plan.var_col[other[0]] == 6
-    anc = plan_from_refs(np.array([2]), np.array([1]), np.array([0, 1]), 8, np.array([3]))
+    anc = plan_from_refs(np.array([2, 2, 5, 6]), np.array([1, 0, 1, 1]), np.array([0, 1, 2, 3, 4]), 8, np.array([3, 1, 0, 9]))
+    k01, rng, other = anc.fast_tables()
+    assert k01 is None and rng.shape == (8, 2)
+    assert rng[2].tolist() == [0, 2] and rng[5].tolist() == [2, 1] and rng[6].tolist() == [0, 0]  # label 9 -> other
+    assert other.tolist() == [2]
     ck, other = anc.biallelic_tables()
-    assert (ck == -1).all() and other.tolist() == [0]
+    assert (ck == -1).all() and len(other) == anc.n_vars
 
 
 def test_plan_from_refs_dedups_and_validates():
