@@ -216,6 +216,26 @@ int ht_synth_ancestry(uint8_t* anc, int64_t s_samp, int64_t s_var, int64_t s_str
                       uint32_t n_pops, uint32_t tract_len, void* stream);
 
 /*
+ * Local-ancestry labels from breakpoint blocks -- Breakpoints.population_array /
+ * _find_blocks (haptools/data/breakpoints.py:225-330), the producer of the ancestry matrix
+ * that `transform --ancestry` uses when a .bp file exists (haptools/transform.py:644-660).
+ *   blk_key[B]      (chromosome index << 32) | end position of every block; the blocks of
+ *                   (sample s, strand c) are blk_key[seg_off[2s+c] .. seg_off[2s+c+1]-1],
+ *                   ascending.
+ *   blk_pop[B]      encoded population label of every block (Breakpoints.encode).
+ *   var_key[p]      (chromosome index << 32) | position of every variant.
+ *   anc             output labels, element (s, v, c) at anc + s*s_samp + v*s_var + c*s_strand:
+ *                   the label of the first block whose end position is >= the variant's
+ *                   (np.searchsorted side="left") on the variant's chromosome, 255 if none.
+ *   bad             optional uint64, initialised to ~0 by the caller: receives the minimum of
+ *                   ((2s + c) << 32 | v) over the (strand, variant) pairs without a block.
+ */
+int ht_bp_ancestry(const uint64_t* blk_key, const uint8_t* blk_pop, const uint32_t* seg_off,
+                   const uint64_t* var_key, uint8_t* anc, int64_t s_samp, int64_t s_var,
+                   int64_t s_strand, int64_t n_samples, int64_t n_vars, uint64_t* bad,
+                   void* stream);
+
+/*
  * Host <-> device plumbing for the Python host layer (GenotypesPLINK-style chunked input,
  * haptools/data/genotypes.py:1353-1406, and strided result read-back): a pitched 2-D copy
  * (cudaMemcpy2DAsync; `kind` = HT_COPY_*) and page-locking of an existing host range, so that

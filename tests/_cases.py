@@ -64,7 +64,33 @@ def load_case(path) -> dict:
 
 
 def list_golden() -> list[Path]:
-    return sorted(GOLDEN_DIR.glob("*.npz"))
+    """Transform fixtures (the bp_*.npz breakpoint fixtures have their own loader)."""
+    return sorted(p for p in GOLDEN_DIR.glob("*.npz") if not p.name.startswith("bp_"))
+
+
+def list_golden_bp() -> list[Path]:
+    return sorted(GOLDEN_DIR.glob("bp_*.npz"))
+
+
+def load_bp_case(path, breakpoints_cls, hapblock_dtype):
+    """Rebuild a Breakpoints object (un-encoded) + the variants array from a bp_*.npz fixture."""
+    with np.load(path, allow_pickle=False) as z:
+        meta = json.loads(str(z["meta"]))
+        n = int(z["n"])
+        data = {}
+        for s in range(n):
+            strands = []
+            for c in range(2):
+                sel = (z["blk_sample"] == s) & (z["blk_strand"] == c)
+                rows = [(str(pop), str(chrom), int(bp), float(bp) / 1e4)
+                        for pop, chrom, bp in zip(z["blk_pop"][sel], z["blk_chrom"][sel], z["blk_bp"][sel])]
+                strands.append(np.array(rows, dtype=hapblock_dtype))
+            data[f"S{s}"] = strands
+        variants = np.array(list(zip(z["var_chrom"], z["var_pos"])), dtype=[("chrom", "U10"), ("pos", np.uint32)])
+        expected = z["expected"]
+    bps = breakpoints_cls(fname=None)
+    bps.data = data
+    return bps, variants, meta, expected
 
 
 def build_objects(case: dict, ns, with_alleles: bool = True):
