@@ -12,7 +12,7 @@ import os
 
 # HT_LIB_PATH lets experiments (profiles/) load an alternative build of the same ABI
 LIB_PATH = Path(os.environ.get("HT_LIB_PATH") or Path(__file__).resolve().parent / "libhaptools_cuda.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
 HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
@@ -44,7 +44,7 @@ SIGNATURES = {
     "ht_plane_bytes": (_sz, [_i64, _i64]),
     "ht_pack_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p]),
     "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
-    "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p]),
+    "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
     "ht_count_bits": (_i32, [_p, _i64, _i64, _p, _p]),
     "ht_synth_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _p]),

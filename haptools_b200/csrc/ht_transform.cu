@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(kThreads, 4)
 transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                     const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
                     int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0,
-                    uint8_t* __restrict__ out, int64_t out_s_samp) {
+                    uint8_t* __restrict__ out, int64_t out_s_samp,
+                    unsigned long long* __restrict__ counts) {
     __shared__ __align__(16) uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
     __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
     __shared__ uint32_t s_off[kHapBlock + 1];                  // CSR offsets of the block
@@ -254,6 +255,17 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
         const uint2 r = park[i * 32];
         a[2 * i] = r.x;
         a[2 * i + 1] = r.y;
+    }
+    if (counts) {
+        // allele counts for check_maf (haptools/data/genotypes.py:559-625), fused: popcount of
+        // my word of every result, one warp reduction and one atomic per haplotype and tile
+        const int64_t rem = n_samples - tile * kTileSamples - 32 * (int64_t)lane;
+        const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+#pragma unroll
+        for (int i = 0; i < kHapsPerWarp; ++i) {
+            const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(a[2 * i] & vm) + __popc(a[2 * i + 1] & vm));
+            if (lane == 0 && hl_begin + i < hl_end && c) atomicAdd(counts + h0 + hl_begin + i, (unsigned long long)c);
+        }
     }
     __syncwarp();
 
@@ -371,10 +383,13 @@ extern "C" {
 
 int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                     const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
-                    uint8_t* out, int64_t out_s_samp, void* stream) {
+                    uint8_t* out, int64_t out_s_samp, uint64_t* counts, void* stream) {
     using namespace ht;
     if (int rc = check_common(planes, n_samples, n_keys, hap_off, hap_key, n_haps)) return rc;
+    if (counts && n_haps > 0)
+        HT_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(uint64_t) * (size_t)n_haps, (cudaStream_t)stream));
     if (n_samples == 0 || n_haps == 0) return HT_OK;
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
     if (!out) return bad_arg("out is NULL");
     if (out_s_samp < 2 * n_haps) return bad_arg("out_s_samp < 2 * n_haps");
     // with no keys at all every haplotype is empty; the kernel then never touches `planes`
@@ -395,13 +410,13 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
         cudaStream_t st = (cudaStream_t)stream;
         if (vec == 16)
             transform_u8_kernel<16><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
-                                                             n_haps, (uint32_t)n_hb, t0, out, out_s_samp);
+                                                             n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         else if (vec == 2)
             transform_u8_kernel<2><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
-                                                            n_haps, (uint32_t)n_hb, t0, out, out_s_samp);
+                                                            n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         else
             transform_u8_kernel<1><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
-                                                            n_haps, (uint32_t)n_hb, t0, out, out_s_samp);
+                                                            n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         HT_CUDA_TRY(cudaGetLastError());
     }
     return HT_OK;

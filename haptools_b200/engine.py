@@ -108,12 +108,13 @@ def pack(dplan: DevicePlan, gt_ptr: int, gt_strides, n_samples: int, planes: tor
 
 
 def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_ptr: int, pitch: int,
-                 stream=None) -> None:
-    """K2 on raw device pointers."""
+                 stream=None, counts: torch.Tensor = None) -> None:
+    """K2 on raw device pointers.  `counts` (optional int64[H] tensor) receives the number of
+    present copies of every haplotype (the numerator of check_maf)."""
     check(
         _cuda.lib().ht_transform_u8(
             _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
-            dplan.n_haps, out_ptr, pitch, _stream_ptr(stream),
+            dplan.n_haps, out_ptr, pitch, _ptr(counts), _stream_ptr(stream),
         ),
         "ht_transform_u8",
     )
@@ -145,9 +146,18 @@ def _check_gt_tensor(gt: torch.Tensor, what: str) -> None:
         raise ValueError(f"{what} must have shape (samples, variants, >=2) and dtype uint8 or bool")
 
 
+def maf_from_counts(counts, n_samples: int) -> np.ndarray:
+    """Minor allele frequency of each haplotype from its allele count, exactly as
+    Genotypes.check_maf computes it (haptools/data/genotypes.py:600-602)."""
+    counts = counts.cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)
+    ref_af = counts / (2 * n_samples)
+    return np.array([ref_af, 1 - ref_af]).min(axis=0)
+
+
 def transform_device(gt: torch.Tensor, dplan: DevicePlan, ancestry: torch.Tensor = None,
                      out: torch.Tensor = None, planes: torch.Tensor = None, fmt: str = "u8",
-                     flags: torch.Tensor = None, pack_mode: int = _cuda.HT_PACK_AUTO):
+                     flags: torch.Tensor = None, pack_mode: int = _cuda.HT_PACK_AUTO,
+                     counts: torch.Tensor = None):
     """
     Transform genotypes resident on the device.
 
@@ -186,7 +196,7 @@ def transform_device(gt: torch.Tensor, dplan: DevicePlan, ancestry: torch.Tensor
         else:
             if out.dtype != torch.uint8 or tuple(out.shape) != (n, H, 2) or (H and out.stride()[1:] != (2, 1)):
                 raise ValueError("out must be a uint8 tensor of shape (n, H, 2) with contiguous rows")
-        transform_u8(dplan, planes, n, out.data_ptr(), int(out.stride(0)) if n else 2 * H)
+        transform_u8(dplan, planes, n, out.data_ptr(), int(out.stride(0)) if n else 2 * H, counts=counts)
         return out
 
 

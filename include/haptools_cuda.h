@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define HT_ABI_VERSION 5
+#define HT_ABI_VERSION 6
 
 #define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
 #define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
@@ -171,10 +171,14 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
  *           0x00 or 0x01 (numpy bool bytes).  A haplotype without keys yields 0x01
  *           (np.all over an empty axis).  out_s_samp >= 2*H.  Rows >= n_samples are not
  *           touched.
+ *   counts  optional (may be NULL) uint64[H], overwritten: number of 1-bytes of each
+ *           haplotype over all samples and both strands -- the allele counts that
+ *           `hap_gts.check_maf` (genotypes.py:559-625; transform.py:671-673) derives with a
+ *           second pass over the result; here they fall out of the kernel (popcount).
  */
 int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                     const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
-                    uint8_t* out, int64_t out_s_samp, void* stream);
+                    uint8_t* out, int64_t out_s_samp, uint64_t* counts, void* stream);
 
 /*
  * K2, bit-packed result: out_bits has the plane layout with haplotypes in place of keys

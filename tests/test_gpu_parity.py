@@ -302,6 +302,22 @@ def test_bits_and_counts(n, p, H):
     np.testing.assert_array_equal(counts.cpu().numpy(), want.sum(axis=(0, 2)))
 
 
+def test_fused_allele_counts_and_maf():
+    """check_maf's allele counts fall out of the transform kernel (N2)."""
+    rng = np.random.default_rng(12)
+    for n, p, H in ((2504, 64, 300), (1000, 16, 7)):
+        gt, _, plan, want = _random_arrays(rng, n, p, H, max_k=3)
+        dplan = engine.DevicePlan(plan)
+        counts = torch.full((H,), -7, dtype=torch.int64, device="cuda")
+        out = engine.transform_device(torch.from_numpy(gt).cuda(), dplan, counts=counts)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
+        np.testing.assert_array_equal(counts.cpu().numpy(), want.sum(axis=(0, 2)))
+        # the reference's formula (haptools/data/genotypes.py:600-602) on the host result
+        ref_af = want.astype(np.bool_).sum(axis=(0, 2)) / (2 * n)
+        np.testing.assert_array_equal(engine.maf_from_counts(counts, n), np.array([ref_af, 1 - ref_af]).min(axis=0))
+
+
 # ------------------------------------------------------------------ pgenlib int32 buffers
 def test_pack_i32_chunks():
     rng = np.random.default_rng(11)
