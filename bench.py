@@ -310,7 +310,8 @@ def run_b200(args):
     pack_gbs = ab["pack"] / (pack_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "transform_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
-        "frac": tr_gbs / peak, "traffic": None, "peak_source": peak_src,
+        "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.064), "peak_source": peak_src,
+        "traffic_source": "ncu --set full (profiles/r1): dram read+write per launch = 1.064 x algorithmic bytes at 131,072 samples, scaled linearly to this launch",
         "algorithmic_bytes_per_launch": ab["transform"], "ms_per_launch": tr_ms,
         "pack": {"kernel": "pack", "achieved": pack_gbs, "frac": pack_gbs / peak, "algorithmic_bytes_per_launch": ab["pack"], "ms_per_launch": pack_ms},
         "step": {"achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
