@@ -49,6 +49,7 @@ SIGNATURES = {
     "ht_count_bits": (_i32, [_p, _i64, _i64, _p, _p]),
     "ht_synth_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _p]),
     "ht_synth_ancestry": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _u32, _u32, _p]),
+    "ht_relayout_u8": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p]),
     "ht_bp_ancestry": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "ht_copy2d": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i32, _p]),
     "ht_host_register": (_i32, [_p, _sz]),

@@ -74,6 +74,30 @@ __global__ void __launch_bounds__(256) synth_kernel(const SynthArgs a, bool vari
     }
 }
 
+// dst(s, v, c) = src(s, v, c) for c in {0, 1}: re-layout of a strided genotype chunk (e.g. the
+// reference's arrays that still interleave the phase column) into the dense
+// 2-bytes-per-genotype form the fast pack kernels read.  Only used on host-fed chunks, where
+// PCIe, not HBM, is the bound.
+struct RelayoutArgs {
+    const uint8_t* src;
+    int64_t ss, sv, sc;
+    uint8_t* dst;
+    int64_t ds, dv;
+    int64_t n, p;
+};
+
+__global__ void __launch_bounds__(256) relayout_kernel(const RelayoutArgs a, bool variant_fast) {
+    const int64_t total = a.n * a.p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = variant_fast ? i / a.p : i % a.n;
+        const int64_t v = variant_fast ? i % a.p : i / a.n;
+        const uint8_t* in = a.src + s * a.ss + v * a.sv;
+        const uint16_t g = (uint16_t)in[0] | ((uint16_t)in[a.sc] << 8);
+        *reinterpret_cast<uint16_t*>(a.dst + s * a.ds + v * a.dv) = g;
+    }
+}
+
 static int launch_synth(SynthArgs a, bool ancestry, void* stream) {
     if (a.n < 0 || a.p < 0) return bad_arg("negative size");
     if (a.n == 0 || a.p == 0) return HT_OK;
@@ -101,6 +125,22 @@ int ht_synth_gt(uint8_t* gt, int64_t s_samp, int64_t s_var, int64_t s_strand, in
     SynthArgs a{gt, s_samp, s_var, s_strand, n_samples, n_vars, sample_offset, seed, mode,
                 missing_per_64k, 0u};
     return launch_synth(a, false, stream);
+}
+
+int ht_relayout_u8(const uint8_t* src, int64_t s_samp, int64_t s_var, int64_t s_strand, int64_t n_samples,
+                   int64_t n_vars, uint8_t* dst, int64_t d_samp, int64_t d_var, void* stream) {
+    using namespace ht;
+    if (n_samples < 0 || n_vars < 0) return bad_arg("negative size");
+    if (n_samples == 0 || n_vars == 0) return HT_OK;
+    if (!src || !dst) return bad_arg("ht_relayout_u8: NULL pointer");
+    if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)d_samp | (uintptr_t)d_var) & 1) != 0)
+        return bad_arg("ht_relayout_u8: destination must be 2-byte aligned with even strides");
+    RelayoutArgs a{src, s_samp, s_var, s_strand, dst, d_samp, d_var, n_samples, n_vars};
+    const int64_t total = n_samples * n_vars;
+    const int64_t blocks = min((total + 255) / 256, (int64_t)148 * 64);
+    relayout_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, d_var <= d_samp);
+    HT_CUDA_TRY(cudaGetLastError());
+    return HT_OK;
 }
 
 int ht_synth_ancestry(uint8_t* anc, int64_t s_samp, int64_t s_var, int64_t s_strand,

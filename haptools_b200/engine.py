@@ -203,6 +203,12 @@ def transform_device(gt: torch.Tensor, dplan: DevicePlan, ancestry: torch.Tensor
 # --------------------------------------------------------------------------------------
 # host arrays
 # --------------------------------------------------------------------------------------
+def _fast_layout(strides) -> bool:
+    """Do these device strides (sample, variant, strand) reach one of the fast pack kernels?"""
+    ss, sv, sc = strides
+    return sc == 1 and ((sv == 2 and ss % 16 == 0) or (ss == 2 and sv % 16 == 0))
+
+
 class _Region:
     """The bytes of a[s0:s1, :, :2] as a pitched 2-D region of host memory."""
 
@@ -217,6 +223,14 @@ class _Region:
 
     def dev_bytes(self) -> int:
         return self.rows * self.dev_pitch()
+
+    def dense(self, n: int, p: int):
+        """(strides, bytes) of the dense 2-bytes-per-genotype re-layout with the same major
+        axis and 16-byte aligned rows (ht_relayout_u8 target)."""
+        inner = p if self.sample_major else n
+        pitch = max(16, (2 * inner + 15) // 16 * 16)
+        strides = (pitch, 2, 1) if self.sample_major else (2, pitch, 1)
+        return strides, pitch * (n if self.sample_major else p)
 
 
 def _region(a: np.ndarray, s0: int, s1: int) -> _Region:
@@ -316,6 +330,7 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
         cur = torch.cuda.current_stream(dev)
         for s in (s_in, s_cmp, s_out):
             s.wait_stream(cur)
+        dense_gt = dense_anc = None  # scratch of the on-device re-layout (compute stream only)
         ev_h2d = [None] * nbuf
         ev_cmp = [None] * nbuf
         ev_d2h = [None] * nbuf
@@ -341,8 +356,26 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
             s_cmp.wait_event(ev_h2d[b])
             if ev_d2h[b] is not None:
                 s_cmp.wait_event(ev_d2h[b])
-            pack(dplan, gt_buf[b].data_ptr(), rg.dev_strides(), rows, planes,
-                 _ptr(anc_buf[b]) if ra else 0, ra.dev_strides() if ra else (0, 0, 0), None, pack_mode, s_cmp)
+            g_ptr, g_str = gt_buf[b].data_ptr(), rg.dev_strides()
+            a_ptr, a_str = (_ptr(anc_buf[b]), ra.dev_strides()) if ra else (0, (0, 0, 0))
+            if pack_mode == _cuda.HT_PACK_AUTO:
+                # arrays that interleave the phase column (or other odd strides): dense re-layout
+                # on the device so that the fast pack kernels apply (PCIe is the bound here)
+                if not _fast_layout(g_str):
+                    d_str, d_bytes = rg.dense(rows, p)
+                    if dense_gt is None or dense_gt.numel() < d_bytes:
+                        dense_gt = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
+                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, p, dense_gt.data_ptr(),
+                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    g_ptr, g_str = dense_gt.data_ptr(), d_str
+                if ra and not _fast_layout(a_str):
+                    d_str, d_bytes = ra.dense(rows, p)
+                    if dense_anc is None or dense_anc.numel() < d_bytes:
+                        dense_anc = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
+                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, p, dense_anc.data_ptr(),
+                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    a_ptr, a_str = dense_anc.data_ptr(), d_str
+            pack(dplan, g_ptr, g_str, rows, planes, a_ptr, a_str, None, pack_mode, s_cmp)
             transform_u8(dplan, planes, rows, out_buf[b].data_ptr(), pitch, s_cmp)
             ev_cmp[b] = s_cmp.record_event()
             # D2H

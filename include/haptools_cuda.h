@@ -220,6 +220,18 @@ int ht_synth_ancestry(uint8_t* anc, int64_t s_samp, int64_t s_var, int64_t s_str
                       uint32_t n_pops, uint32_t tract_len, void* stream);
 
 /*
+ * Re-layout of a strided genotype (or ancestry) chunk on the device:
+ * dst(s, v, c) = src(s, v, c) for c in {0, 1}, with dst element (s, v, c) at
+ * dst + s*d_samp + v*d_var + c.  Used by the host pipeline to turn the reference's layouts
+ * that interleave the phase column (strides (3p, 3, 1) from the PGEN reader, (3, 3n, 1) from
+ * the VCF reader, haptools/data/genotypes.py:183-210, 1346-1352, 557) into the dense form the
+ * fast pack kernels read.
+ */
+int ht_relayout_u8(const uint8_t* src, int64_t s_samp, int64_t s_var, int64_t s_strand,
+                   int64_t n_samples, int64_t n_vars, uint8_t* dst, int64_t d_samp, int64_t d_var,
+                   void* stream);
+
+/*
  * Local-ancestry labels from breakpoint blocks -- Breakpoints.population_array /
  * _find_blocks (haptools/data/breakpoints.py:225-330), the producer of the ancestry matrix
  * that `transform --ancestry` uses when a .bp file exists (haptools/transform.py:644-660).

@@ -389,6 +389,34 @@ def test_host_pipeline_chunked(lay):
     np.testing.assert_array_equal(chunked, want)
 
 
+def test_relayout_kernel_and_phase_column_layouts_take_the_fast_path(monkeypatch):
+    """Arrays that interleave the phase column are re-laid-out on the device and then packed by
+    the fast kernels (never by the generic one)."""
+    rng = np.random.default_rng(6)
+    n, p, H = 2100, 40, 33
+    gt, _, plan, want = _random_arrays(rng, n, p, H, missing=0.02)
+    modes = []
+    real_pack = engine.pack
+
+    def spy(dplan, gt_ptr, gt_strides, *a, **kw):
+        modes.append(tuple(int(x) for x in gt_strides))
+        return real_pack(dplan, gt_ptr, gt_strides, *a, **kw)
+
+    monkeypatch.setattr(engine, "pack", spy)
+    for lay in ("C3", "F3"):
+        np.testing.assert_array_equal(engine.transform_host(_layouts(gt)[lay], plan), want)
+    assert all(engine._fast_layout(st) for st in modes), modes
+    # the kernel itself, both directions
+    src = torch.from_numpy(np.ascontiguousarray(_layouts(gt)["C3"].base if _layouts(gt)["C3"].base is not None else gt)).cuda()
+    c3 = _to_device_keep_strides(_layouts(gt)["C3"])
+    dst = torch.zeros((n, 96), dtype=torch.uint8, device="cuda")
+    _cuda.check(_cuda.lib().ht_relayout_u8(c3.data_ptr(), *c3.stride(), n, p, dst.data_ptr(), 96, 2, 0), "relayout")
+    np.testing.assert_array_equal(dst[:, : 2 * p].cpu().numpy().reshape(n, p, 2), gt)
+    dstv = torch.zeros((p, 2 * n + 8), dtype=torch.uint8, device="cuda")
+    _cuda.check(_cuda.lib().ht_relayout_u8(c3.data_ptr(), *c3.stride(), n, p, dstv.data_ptr(), 2, 2 * n + 8, 0), "relayout")
+    np.testing.assert_array_equal(dstv[:, : 2 * n].cpu().numpy().reshape(p, n, 2).transpose(1, 0, 2), gt)
+
+
 def test_host_exotic_strides():
     rng = np.random.default_rng(4)
     gt, _, plan, want = _random_arrays(rng, 300, 20, 30)
