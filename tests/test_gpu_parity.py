@@ -246,6 +246,32 @@ def test_ancestry_label_ranges_sample_major(case):
         np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=mode)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_host_api_vs_oracle(seed):
+    """Randomised differential test through the host-array API: random shapes, physical
+    layouts, dtype, key mix (multi-allelic, missing, ancestry with small/large labels, empty and
+    long haplotypes), chunking -- always bit-exact against the oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([1, 7, 33, 200, 1024, 1500, 2100, 4097]))
+    p = int(rng.integers(1, 90))
+    H = int(rng.choice([1, 3, 8, 17, 128, 130, 400]))
+    anc_kind = int(rng.integers(0, 3))  # 0 none, 1 labels < 8, 2 labels up to 19
+    gt, anc, plan, want = _random_arrays(
+        rng, n, p, H, max_k=int(rng.integers(1, 8)), multi=bool(rng.integers(0, 2)),
+        missing=float(rng.choice([0.0, 0.0, 0.01, 0.2])), n_pops=[0, 5, 20][anc_kind],
+        long_hap=int(rng.choice([0, 0, 60])),
+    )
+    lay = str(rng.choice(["C", "F", "C3", "F3"]))
+    arr = _layouts(gt)[lay]
+    if anc is None and rng.integers(0, 3) == 0 and gt.max() <= 1:
+        arr = arr.astype(np.bool_)  # check_biallelic output (haptools/data/genotypes.py:528)
+    a = _layouts(anc)[lay] if anc is not None else None
+    chunk = int(rng.choice([0, 1024, 2048])) or None
+    got = engine.transform_host(arr, plan, ancestry=a, chunk_samples=chunk)
+    assert got.dtype == np.bool_ and got.flags.c_contiguous
+    np.testing.assert_array_equal(got, want)
+
+
 def test_long_haplotype_unstaged_keys():
     """A haplotype block whose key list exceeds the shared-memory stage (3072 keys)."""
     rng = np.random.default_rng(5)
