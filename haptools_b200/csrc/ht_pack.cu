@@ -216,6 +216,45 @@ pack_vm_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
     }
     publish_flags(a.flags, fl);
 
+    if (!kAnc) {
+        // Biallelic single pass: if the variant's keys are just alleles {0, 1} and no byte of the
+        // row is >= 2, the allele-1 plane is the bytes' low bit and the allele-0 plane its
+        // complement.  8 samples of a strand are gathered with one carry-free multiply:
+        // u = lsb(s0..s3) | lsb(s4..s7) << 4 has its bits at 8i and 8i + 4; times 0x00204081 they
+        // land contiguously at bits 21..28.
+        const uint32_t nk = ke - kb;
+        const uint32_t al0 = nk >= 1 ? __ldg(a.key_allele + kb) : 0u;
+        const uint32_t al1 = nk >= 2 ? __ldg(a.key_allele + kb + 1) : 1u;
+        uint32_t d = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d |= (y[j][0] | y[j][1]) | (z[j][0] | z[j][1]);
+        const bool dirty = __any_sync(0xffffffffu, (d & 0xfefefefeu) != 0u);
+        if (nk <= 2 && al0 <= 1u && al1 <= 1u && !dirty) {
+            // keys are sorted by allele: (0), (1) or (0, 1)
+            const int k_ref = al0 == 0u ? (int)kb : -1;
+            const int k_alt = al0 == 1u ? (int)kb : (nk == 2 ? (int)kb + 1 : -1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u0 = (y[j][0] & 0x01010101u) + ((y[j][1] & 0x01010101u) << 4);
+                const uint32_t u1 = (z[j][0] & 0x01010101u) + ((z[j][1] & 0x01010101u) << 4);
+                const uint32_t m0 = ((u0 * 0x00204081u) >> 21) & 0xffu;  // 8 samples, strand 0
+                const uint32_t m1 = ((u1 * 0x00204081u) >> 21) & 0xffu;  // 8 samples, strand 1
+                uint32_t t = (m0 | (m1 << 16)) << (8 * (lane & 1));
+                t |= __shfl_xor_sync(0xffffffffu, t, 1);
+                const uint32_t u = __shfl_xor_sync(0xffffffffu, t, 2);
+                const uint32_t lo = (lane & 2) ? u : t, hi = (lane & 2) ? t : u;
+                if ((lane & 3) == 0) {
+                    const int word = 8 * j + (lane >> 2);
+                    const uint32_t vm = valid_mask(a.n, tile, word);
+                    const uint32_t w0 = prmt(lo, hi, 0x5410), w1 = prmt(lo, hi, 0x7632);
+                    if (k_alt >= 0) record(a, tile, (uint32_t)k_alt)[word] = make_uint2(w0 & vm, w1 & vm);
+                    if (k_ref >= 0) record(a, tile, (uint32_t)k_ref)[word] = make_uint2(~w0 & vm, ~w1 & vm);
+                }
+            }
+            return;
+        }
+    }
+
     for (uint32_t k = kb; k < ke; ++k) {
         const uint32_t pat = (uint32_t)__ldg(a.key_allele + k) * 0x01010101u;
         const uint32_t lpat = kAnc ? (uint32_t)__ldg(a.key_label + k) * 0x01010101u : 0u;

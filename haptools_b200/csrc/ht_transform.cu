@@ -32,6 +32,7 @@ constexpr int kThreads = kWarps * 32;             // 256
 constexpr int kStageKeys = 3072;    // key indices staged per CTA (12 KB, each haplotype's list
                                     // padded to a multiple of 4); longer blocks read their
                                     // lists straight from global memory
+constexpr int kTilesPerCta = 1;     // consecutive tiles per CTA (key lists staged once)
 constexpr int kUPitch = kTileSamples + 4;  // +4 words: the 8 warps' rows land in distinct banks
 
 __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
@@ -72,30 +73,36 @@ __device__ __forceinline__ uint2 and_keys_global(const uint2* __restrict__ tile_
     return make_uint2(r0, r1);
 }
 
-// Staged key quads: bits 31/30 of the FIRST key of a quad carry flags.
-constexpr uint32_t kQuadLast = 0x80000000u;  // last quad of its haplotype: emit the result
-constexpr uint32_t kQuadSkip = 0x40000000u;  // stands for a haplotype without alleles
-constexpr uint32_t kKeyMask = 0x3fffffffu;
+// Staged key quads hold BYTE offsets of the keys' records inside a tile (key * 256); the low
+// bits of the FIRST entry of a quad carry flags.  (Needs n_keys < 2^24; else unstaged path.)
+constexpr uint32_t kQuadLast = 1u;  // last quad of its haplotype: emit the result
+constexpr uint32_t kQuadSkip = 2u;  // stands for a haplotype without alleles
+constexpr uint32_t kOffMask = 0xffffff00u;
+constexpr int64_t kMaxStagedKeys = 1 << 24;
 
 struct Batch {  // two quads = 8 plane records in flight
     uint2 v[8];
     uint32_t f0, f1;  // flag words of the two quads
 };
 
-__device__ __forceinline__ void load_batch(const uint2* __restrict__ tile_rec,
+__device__ __forceinline__ uint2 ld_rec(const char* tile_bytes, uint32_t off) {
+    return ld_plane(reinterpret_cast<const uint2*>(tile_bytes + off));
+}
+
+__device__ __forceinline__ void load_batch(const char* __restrict__ tile_bytes,
                                            const uint4* __restrict__ quads, uint32_t q,
                                            uint32_t q_last, Batch& b) {
     const uint4 ka = quads[q], kb = quads[min(q + 1, q_last)];
     b.f0 = ka.x;
     b.f1 = kb.x;
-    b.v[0] = ld_plane(tile_rec + (size_t)(ka.x & kKeyMask) * kTileWords);
-    b.v[1] = ld_plane(tile_rec + (size_t)ka.y * kTileWords);
-    b.v[2] = ld_plane(tile_rec + (size_t)ka.z * kTileWords);
-    b.v[3] = ld_plane(tile_rec + (size_t)ka.w * kTileWords);
-    b.v[4] = ld_plane(tile_rec + (size_t)(kb.x & kKeyMask) * kTileWords);
-    b.v[5] = ld_plane(tile_rec + (size_t)kb.y * kTileWords);
-    b.v[6] = ld_plane(tile_rec + (size_t)kb.z * kTileWords);
-    b.v[7] = ld_plane(tile_rec + (size_t)kb.w * kTileWords);
+    b.v[0] = ld_rec(tile_bytes, ka.x & kOffMask);
+    b.v[1] = ld_rec(tile_bytes, ka.y);
+    b.v[2] = ld_rec(tile_bytes, ka.z);
+    b.v[3] = ld_rec(tile_bytes, ka.w);
+    b.v[4] = ld_rec(tile_bytes, kb.x & kOffMask);
+    b.v[5] = ld_rec(tile_bytes, kb.y);
+    b.v[6] = ld_rec(tile_bytes, kb.z);
+    b.v[7] = ld_rec(tile_bytes, kb.w);
 }
 
 __device__ __forceinline__ void consume_quad(const uint2* v, uint32_t flags, uint32_t& r0,
@@ -116,7 +123,7 @@ __device__ __forceinline__ void consume_quad(const uint2* v, uint32_t flags, uin
 // idempotent; a haplotype without alleles gets one "skip" quad), so the warp walks them as
 // ONE stream, two quads (8 records of 256 B) per step, always with the next step's 8 reads
 // already in flight; a haplotype's result is emitted when its last quad is consumed.
-__device__ __forceinline__ void and_phase_staged(const uint2* __restrict__ tile_rec,
+__device__ __forceinline__ void and_phase_staged(const char* __restrict__ tile_rec,
                                                  const uint4* __restrict__ quads, uint32_t q,
                                                  uint32_t q_end, uint2* park) {
     if (q >= q_end) return;
@@ -136,6 +143,33 @@ __device__ __forceinline__ void and_phase_staged(const uint2* __restrict__ tile_
         if (q + 1 < q_end) consume_quad(B.v + 4, B.f1, r0, r1, park);
         q += 2;
         if (q >= q_end) break;
+    }
+}
+
+// transpose32 (ht_common.cuh) with the 16- and 8-bit stages done by PRMT (2 instructions per
+// word pair instead of 5)
+__device__ __forceinline__ void transpose32_dev(uint32_t (&a)[32]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t lo = a[k], hi = a[k + 16];
+        a[k] = __byte_perm(lo, hi, 0x5410);
+        a[k + 16] = __byte_perm(lo, hi, 0x7632);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k = (k + 8 + 1) & ~8) {
+        const uint32_t lo = a[k], hi = a[k + 8];
+        a[k] = __byte_perm(lo, hi, 0x6240);
+        a[k + 8] = __byte_perm(lo, hi, 0x7351);
+    }
+    uint32_t m = 0x0f0f0f0fu;
+#pragma unroll
+    for (int j = 4; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= (t << j);
+            a[k + j] ^= t;
+        }
     }
 }
 
@@ -166,7 +200,10 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int64_t tile = tile0 + blockIdx.x / n_hap_blocks;
+    // a CTA handles kTilesPerCta consecutive tiles of one haplotype block: the key lists are
+    // staged once and reused
+    const int64_t tile_first = tile0 + (int64_t)(blockIdx.x / n_hap_blocks) * kTilesPerCta;
+    const int64_t n_tiles_all = (n_samples + kTileSamples - 1) / kTileSamples;
     const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
     const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
 
@@ -202,7 +239,7 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
     const uint32_t w_kb = hl_begin < hl_end ? s_off[hl_begin] : 0u;
     const uint32_t w_cnt = hl_begin < hl_end ? s_off[hl_end] - w_kb : 0u;
     const bool staged = s_quad[kHapBlock] * 4u <= (uint32_t)kStageKeys && n_keys > 0 &&
-                        w_cnt <= (uint32_t)kTileSamples;
+                        n_keys < kMaxStagedKeys && w_cnt <= (uint32_t)kTileSamples;
     if (staged) {
 #pragma unroll 1
         for (uint32_t j = lane; j < w_cnt; j += 128) {
@@ -224,102 +261,113 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
             const uint32_t base = 4u * s_quad[hl], padded = max(4u, (len + 3u) & ~3u);
 #pragma unroll 1
             for (uint32_t j = lane; j < padded; j += 32) {
-                uint32_t key = len ? my_row[kb + min(j, len - 1)] : 0u;
-                if ((j & 3u) == 0u) key |= (j + 4 >= padded ? kQuadLast : 0u) | (len ? 0u : kQuadSkip);
-                s_keys[base + j] = key;
+                uint32_t off = len ? my_row[kb + min(j, len - 1)] << 8 : 0u;  // byte offset of the record
+                if ((j & 3u) == 0u) off |= (j + 4 >= padded ? kQuadLast : 0u) | (len ? 0u : kQuadSkip);
+                s_keys[base + j] = off;
             }
         }
     }
     __syncwarp();
 
-    // ---- 1. AND ----------------------------------------------------------------------
-    // results are parked in the warp's own slice of s_u (which is only reused for the
-    // exchange after the warp has read everything back): keeps the haplotype loop rolled
-    const uint2* tile_rec =
-        reinterpret_cast<const uint2*>(planes) + ((size_t)tile * (size_t)n_keys) * kTileWords + lane;
     uint2* park = reinterpret_cast<uint2*>(my_row) + lane;
-    if (staged) {
-        if (hl_begin < hl_end)
-            and_phase_staged(tile_rec, reinterpret_cast<const uint4*>(s_keys), s_quad[hl_begin], s_quad[hl_end], park);
-    } else {
+    const uint32_t q_begin = s_quad[hl_begin], q_end = s_quad[hl_end];
+
 #pragma unroll 1
-        for (int hl = hl_begin; hl < hl_end; ++hl) {
-            uint2 r = make_uint2(0xffffffffu, 0xffffffffu);
-            if (n_keys > 0) r = and_keys_global(tile_rec, hap_key, s_off[hl], s_off[hl + 1]);
-            park[(hl - hl_begin) * 32] = r;
+    for (int ti = 0; ti < kTilesPerCta; ++ti) {
+        const int64_t tile = tile_first + ti;
+        if (tile >= n_tiles_all) break;  // uniform over the CTA
+        if (ti) __syncthreads();         // everybody is done reading the exchange buffer
+
+        // ---- 1. AND ------------------------------------------------------------------
+        // results are parked in the warp's own slice of s_u (which is only reused for the
+        // exchange after the warp has read everything back): keeps the haplotype loop rolled
+        const char* tile_bytes = reinterpret_cast<const char*>(planes) +
+                                 ((size_t)tile * (size_t)n_keys) * (kRecordWords * 4) + 8 * lane;
+        if (staged) {
+            if (hl_begin < hl_end)
+                and_phase_staged(tile_bytes, reinterpret_cast<const uint4*>(s_keys), q_begin, q_end, park);
+        } else {
+            const uint2* tile_rec = reinterpret_cast<const uint2*>(tile_bytes);
+#pragma unroll 1
+            for (int hl = hl_begin; hl < hl_end; ++hl) {
+                uint2 r = make_uint2(0xffffffffu, 0xffffffffu);
+                if (n_keys > 0) r = and_keys_global(tile_rec, hap_key, s_off[hl], s_off[hl + 1]);
+                park[(hl - hl_begin) * 32] = r;
+            }
         }
-    }
-    uint32_t a[32];  // a[2*i + c] = haplotype i of this warp, strand c
-#pragma unroll
-    for (int i = 0; i < kHapsPerWarp; ++i) {
-        const uint2 r = park[i * 32];
-        a[2 * i] = r.x;
-        a[2 * i + 1] = r.y;
-    }
-    if (counts) {
-        // allele counts for check_maf (haptools/data/genotypes.py:559-625), fused: popcount of
-        // my word of every result, one warp reduction and one atomic per haplotype and tile
-        const int64_t rem = n_samples - tile * kTileSamples - 32 * (int64_t)lane;
-        const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+        uint32_t a[32];  // a[2*i + c] = haplotype i of this warp, strand c
 #pragma unroll
         for (int i = 0; i < kHapsPerWarp; ++i) {
-            const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(a[2 * i] & vm) + __popc(a[2 * i + 1] & vm));
-            if (lane == 0 && hl_begin + i < hl_end && c) atomicAdd(counts + h0 + hl_begin + i, (unsigned long long)c);
+            const uint2 r = park[i * 32];
+            a[2 * i] = r.x;
+            a[2 * i + 1] = r.y;
         }
-    }
-    __syncwarp();
-
-    // ---- 2. bits over samples -> bits over (haplotype, strand) ------------------------
-    transpose32(a);
-
-    // ---- 3. exchange + expand + store --------------------------------------------------
-    // sample 32*L + j of the tile is kept at slot 32*L + ((j + L) & 31): lanes write distinct
-    // banks here, and the 16 words one warp reads below fall into 16 distinct banks.
-    uint32_t* my_u = my_row + 32 * lane;
+        if (counts) {
+            // allele counts for check_maf (haptools/data/genotypes.py:559-625), fused: popcount
+            // of my word of every result, one warp reduction and one atomic per haplotype and tile
+            const int64_t rem = n_samples - tile * kTileSamples - 32 * (int64_t)lane;
+            const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
 #pragma unroll
-    for (int j = 0; j < 32; ++j) my_u[(j + lane) & 31] = a[j];
-    __syncthreads();
-
-    const int half = lane & 1;        // low / high 16 bits of the word = haps 0-7 / 8-15
-    const int b = (lane >> 1) & 7;    // which warp's 16 haplotypes
-    const int c0 = warp * 2 + (lane >> 4);  // sample row within each group of 16
-    const int hl0 = b * kHapsPerWarp + half * 8;  // first haplotype (in block) of my 16 bytes
-    const int n_my_haps = min(8, n_blk_haps - hl0);  // may be <= 0
-    if (n_my_haps <= 0) return;  // no barrier below
-    const int64_t s_base = tile * kTileSamples;
-    const int rows = (int)min((int64_t)kTileSamples, n_samples - s_base);
-    const uint32_t* u_col = s_u + b * kUPitch;
-    const int shift = 16 * half;
-    uint8_t* p = out + 2 * (h0 + hl0) + (s_base + c0) * out_s_samp;
-    const int64_t p_step = 16 * out_s_samp;
-
-    if (kOutVec == 16 && n_my_haps == 8 && rows == kTileSamples) {
-        // full tile, full group: two rows (32*L + c0 and 32*L + 16 + c0) per iteration
-#pragma unroll 4
-        for (int L = 0; L < 32; ++L) {
-            const int t = (c0 + L) & 31;
-            const uint32_t w0 = u_col[32 * L + t], w1 = u_col[32 * L + (t ^ 16)];
-            st_stream_v4(p, expand16((w0 >> shift) & 0xffffu));
-            st_stream_v4(p + p_step, expand16((w1 >> shift) & 0xffffu));
-            p += 2 * p_step;
-        }
-        return;
-    }
-#pragma unroll 1
-    for (int it = 0; it < kTileSamples / 16; ++it, p += p_step) {
-        const int sl = it * 16 + c0;
-        if (sl >= rows) break;  // rows only grow with `it`
-        const int L = it >> 1, j = ((it & 1) << 4) + c0;
-        const uint32_t bits = (u_col[32 * L + ((j + L) & 31)] >> shift) & 0xffffu;
-        if (kOutVec == 16 && n_my_haps == 8) {
-            st_stream_v4(p, expand16(bits));
-        } else if (kOutVec >= 2) {
-            for (int q = 0; q < n_my_haps; ++q) {
-                const uint32_t two = (bits >> (2 * q)) & 3u;
-                *reinterpret_cast<uint16_t*>(p + 2 * q) = (uint16_t)((two & 1u) | ((two & 2u) << 7));
+            for (int i = 0; i < kHapsPerWarp; ++i) {
+                const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(a[2 * i] & vm) + __popc(a[2 * i + 1] & vm));
+                if (lane == 0 && hl_begin + i < hl_end && c) atomicAdd(counts + h0 + hl_begin + i, (unsigned long long)c);
             }
-        } else {
-            for (int q = 0; q < 2 * n_my_haps; ++q) p[q] = (uint8_t)((bits >> q) & 1u);
+        }
+        __syncwarp();
+
+        // ---- 2. bits over samples -> bits over (haplotype, strand) --------------------
+        transpose32_dev(a);
+
+        // ---- 3. exchange + expand + store ----------------------------------------------
+        // sample 32*L + j of the tile is kept at slot 32*L + ((j + L) & 31): lanes write
+        // distinct banks here, and the 16 words one warp reads below fall into 16 distinct banks.
+        uint32_t* my_u = my_row + 32 * lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) my_u[(j + lane) & 31] = a[j];
+        __syncthreads();
+
+        // (cheap to recompute per tile; keeping them live across the AND phase costs registers)
+        const int half = threadIdx.x & 1;               // low / high 16 bits of the word = haps 0-7 / 8-15
+        const int b = (threadIdx.x >> 1) & 7;           // which warp's 16 haplotypes
+        const int c0 = (threadIdx.x >> 5) * 2 + ((threadIdx.x >> 4) & 1);  // sample row within each group of 16
+        const int hl0 = b * kHapsPerWarp + half * 8;    // first haplotype (in block) of my 16 bytes
+        const int n_my_haps = min(8, n_blk_haps - hl0);  // may be <= 0
+        const uint32_t* u_col = s_u + b * kUPitch;
+        const int shift = 16 * half;
+        if (n_my_haps <= 0) continue;  // the barriers above are reached by everybody
+        const int64_t s_base = tile * kTileSamples;
+        const int rows = (int)min((int64_t)kTileSamples, n_samples - s_base);
+        uint8_t* p = out + 2 * (h0 + hl0) + (s_base + c0) * out_s_samp;
+        const int64_t p_step = 16 * out_s_samp;
+
+        if (kOutVec == 16 && n_my_haps == 8 && rows == kTileSamples) {
+            // full tile, full group: two rows (32*L + c0 and 32*L + 16 + c0) per iteration
+#pragma unroll 4
+            for (int L = 0; L < 32; ++L) {
+                const int t = (c0 + L) & 31;
+                const uint32_t w0 = u_col[32 * L + t], w1 = u_col[32 * L + (t ^ 16)];
+                st_stream_v4(p, expand16((w0 >> shift) & 0xffffu));
+                st_stream_v4(p + p_step, expand16((w1 >> shift) & 0xffffu));
+                p += 2 * p_step;
+            }
+            continue;
+        }
+#pragma unroll 1
+        for (int it = 0; it < kTileSamples / 16; ++it, p += p_step) {
+            const int sl = it * 16 + c0;
+            if (sl >= rows) break;  // rows only grow with `it`
+            const int L = it >> 1, j = ((it & 1) << 4) + c0;
+            const uint32_t bits = (u_col[32 * L + ((j + L) & 31)] >> shift) & 0xffffu;
+            if (kOutVec == 16 && n_my_haps == 8) {
+                st_stream_v4(p, expand16(bits));
+            } else if (kOutVec >= 2) {
+                for (int q = 0; q < n_my_haps; ++q) {
+                    const uint32_t two = (bits >> (2 * q)) & 3u;
+                    *reinterpret_cast<uint16_t*>(p + 2 * q) = (uint16_t)((two & 1u) | ((two & 2u) << 7));
+                }
+            } else {
+                for (int q = 0; q < 2 * n_my_haps; ++q) p[q] = (uint8_t)((bits >> q) & 1u);
+            }
         }
     }
 }
@@ -370,8 +418,8 @@ static int check_common(const uint32_t* planes, int64_t n_samples, int64_t n_key
     if (n_keys > 0 && !hap_key) return bad_arg("hap_key is NULL");
     if (n_keys > 0 && (reinterpret_cast<uintptr_t>(planes) & 15))
         return bad_arg("planes must be 16-byte aligned");
-    if (n_keys > (int64_t)kKeyMask) {
-        set_error("too many keys (%lld > 2^30 - 1)", (long long)n_keys);
+    if (n_keys > 0xffffffffLL) {
+        set_error("too many keys (%lld)", (long long)n_keys);
         return HT_ERR_UNSUPPORTED;
     }
     return HT_OK;
@@ -402,11 +450,12 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
     const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
     const int vec = ((addr | (uintptr_t)out_s_samp) & 15) == 0 ? 16
                     : ((addr | (uintptr_t)out_s_samp) & 1) == 0 ? 2 : 1;
-    // a grid holds at most 2^31-1 blocks: launch ranges of tiles
-    const int64_t tiles_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
+    // a grid holds at most 2^31-1 blocks: launch ranges of tile groups
+    const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
+    const int64_t tiles_per_launch = groups_per_launch * kTilesPerCta;
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
         const int64_t nt = min(tiles_per_launch, n_tiles - t0);
-        const dim3 grid((unsigned)(nt * n_hb));
+        const dim3 grid((unsigned)(((nt + kTilesPerCta - 1) / kTilesPerCta) * n_hb));
         cudaStream_t st = (cudaStream_t)stream;
         if (vec == 16)
             transform_u8_kernel<16><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,

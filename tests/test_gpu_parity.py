@@ -272,6 +272,23 @@ def test_fuzz_host_api_vs_oracle(seed):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [8, 1024, 2504, 3000])
+def test_variant_major_biallelic_single_pass(n):
+    """Clean biallelic data in the VCF-reader layout: single-pass path of the variant-major
+    kernel (keys (0), (1), (0, 1)); a few dirty variants fall back to the per-key compare."""
+    rng = np.random.default_rng(n)
+    p, H = 50, 64
+    gt, _, plan, want = _random_arrays(rng, n, p, H, multi=False, missing=0.0)
+    out, flags = _run_device(_layouts(gt)["F"], plan, None, "vm")
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
+    assert flags == 0
+    gt[rng.integers(0, n), ::7, :] = 255  # missing calls in every 7th variant
+    want = orc.transform_from_csr(gt, plan.key_col().astype(np.int64), plan.key_allele,
+                                  plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
+    out, _ = _run_device(_layouts(gt)["F"], plan, None, "vm")
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
+
+
 def test_long_haplotype_unstaged_keys():
     """A haplotype block whose key list exceeds the shared-memory stage (3072 keys)."""
     rng = np.random.default_rng(5)
