@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--cpu-samples", type=int, default=0,
                     help="samples of the CPU sample (default: 2048 for the cpu_baseline leg, 512 per process and step for --impl reference)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of --impl reference (0 = all cores, max 16)")
+    ap.add_argument("--sorted-haps", action="store_true",
+                    help="order the synthetic haplotypes by position, as .hap files are after `haptools index` "
+                         "(default: generation order, SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -89,7 +92,8 @@ def _oracle_plan_arrays(w, H):
     from haptools_b200 import synth
     from haptools_b200.plan import plan_from_refs
 
-    ref_col, ref_allele, hap_off, hap_label = synth.synth_haplotype_refs(w["p"], H, w["seed"], n_pops=w["n_pops"])
+    ref_col, ref_allele, hap_off, hap_label = synth.synth_haplotype_refs(
+        w["p"], H, w["seed"], n_pops=w["n_pops"], sort=w.get("sort", False))
     plain = plan_from_refs(ref_col, ref_allele, hap_off, w["p"])
     arrays = (plain.key_col().astype(np.int64), plain.key_allele, plain.hap_off.astype(np.int64), plain.hap_key.astype(np.int64))
     return arrays, (hap_label.astype(np.uint8) if hap_label is not None else None)
@@ -121,6 +125,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = dict(WORKLOADS[args.workload])
+    w["sort"] = bool(args.sorted_haps)
     H = args.haps or w["H"]
     procs = args.cpu_procs or min(os.cpu_count() or 1, 16)
     ns = args.cpu_samples or 512
@@ -218,20 +223,35 @@ def run_b200(args):
     sample_offset = rank * n
 
     # ---- inputs, resident in HBM before the timed region ------------------------------
-    plan = synth.synth_plan(p, H, seed=w["seed"], n_pops=w["n_pops"])
+    w["sort"] = bool(args.sorted_haps)
+    plan = synth.synth_plan(p, H, seed=w["seed"], n_pops=w["n_pops"], sort=w["sort"])
     dplan = engine.DevicePlan(plan, dev)
-    if w["layout"] == "sample_major":
-        gt = torch.empty((n, p, 2), dtype=torch.uint8, device=dev)
-    else:
-        gt = torch.empty((p, n, 2), dtype=torch.uint8, device=dev).permute(1, 0, 2)
-    _cuda.check(lib.ht_synth_gt(gt.data_ptr(), *gt.stride(), n, p, sample_offset, w["seed"] + 1, 1, 0, 0), "synth")
-    anc = None
-    if w["n_pops"]:
-        anc = torch.empty((n, p, 2), dtype=torch.uint8, device=dev)
-        _cuda.check(lib.ht_synth_ancestry(anc.data_ptr(), *anc.stride(), n, p, sample_offset, w["seed"] + 2, w["n_pops"], 2000, 0), "synth_anc")
-    planes = engine.alloc_planes(n, plan.n_keys, dev)
+    def alloc(n):
+        if w["layout"] == "sample_major":
+            gt = torch.empty((n, p, 2), dtype=torch.uint8, device=dev)
+        else:
+            gt = torch.empty((p, n, 2), dtype=torch.uint8, device=dev).permute(1, 0, 2)
+        anc = torch.empty((n, p, 2), dtype=torch.uint8, device=dev) if w["n_pops"] else None
+        planes = engine.alloc_planes(n, plan.n_keys, dev)
+        out = torch.empty((n, engine.out_pitch(H)), dtype=torch.uint8, device=dev)
+        return gt, anc, planes, out
+
+    n_requested = n
+    while True:  # the full UKB-scale shard needs 162.5 GB of HBM: shrink it rather than die
+        try:
+            gt, anc, planes, out = alloc(n)
+            break
+        except torch.cuda.OutOfMemoryError:
+            gt = anc = planes = out = None
+            torch.cuda.empty_cache()
+            if n <= 8192:
+                raise
+            n = (n // 2 + 1023) // 1024 * 1024
+            sample_offset = rank * n
     pitch = engine.out_pitch(H)
-    out = torch.empty((n, pitch), dtype=torch.uint8, device=dev)
+    _cuda.check(lib.ht_synth_gt(gt.data_ptr(), *gt.stride(), n, p, sample_offset, w["seed"] + 1, 1, 0, 0), "synth")
+    if anc is not None:
+        _cuda.check(lib.ht_synth_ancestry(anc.data_ptr(), *anc.stride(), n, p, sample_offset, w["seed"] + 2, w["n_pops"], 2000, 0), "synth_anc")
     torch.cuda.synchronize()
 
     anc_ptr = anc.data_ptr() if anc is not None else 0
@@ -373,7 +393,9 @@ def run_b200(args):
         "dtype": "u8", "data": "synthetic",
         "config": {
             "workload": w["name"], "samples_per_gpu": n, "variants": p, "haplotypes": H,
+            **({"samples_per_gpu_requested": n_requested, "note": "shard shrunk: the requested one did not fit in HBM"} if n != n_requested else {}),
             "haplotype_alleles": plan.n_refs, "distinct_keys": plan.n_keys, "layout": w["layout"],
+            "haplotype_order": "position-sorted" if w["sort"] else "generation order (unsorted)",
             "genotypes": "blocky founders (16 per 64-variant block), device-generated from a counter hash",
             "l2": "inputs (%.1f GB) larger than L2, no flush needed" % (ab["gt"] / 1e9),
             "sharding": "samples, one shard per GPU, no collective on the path",

@@ -73,12 +73,14 @@ def synth_ancestry(n: int, p: int, seed: int, n_pops: int = 5, tract_len: int = 
 
 
 def synth_haplotype_refs(p: int, n_haps: int, seed: int, min_alleles: int = 2, max_alleles: int = 20,
-                         n_pops: int = 0):
+                         n_pops: int = 0, sort: bool = False):
     """
     Flat haplotype definitions: returns (ref_col, ref_allele, hap_off, hap_label|None).
     Haplotype h: k_h ~ U{min..max} distinct variants at strictly increasing columns with gaps
     ~ U{1..4} from a uniformly drawn window start (so the window is <= 4*k_h wide), allele
     index ~ Bernoulli(1/2); with n_pops > 0 also a population label ~ U{0..n_pops-1}.
+    `sort=True` orders the haplotypes by the position of their first variant, the order .hap
+    files have after `haptools index` (tabix needs it); the default keeps generation order.
     """
     rng = np.random.default_rng(seed)
     k = rng.integers(min_alleles, max_alleles + 1, size=n_haps, dtype=np.int64)
@@ -96,6 +98,13 @@ def synth_haplotype_refs(p: int, n_haps: int, seed: int, min_alleles: int = 2, m
     ref_col = start[hap_of_ref] + within
     ref_allele = rng.integers(0, 2, size=K, dtype=np.int64)
     hap_label = rng.integers(0, n_pops, size=n_haps, dtype=np.int64) if n_pops else None
+    if sort:
+        order = np.argsort(ref_col[hap_off[:-1]], kind="stable")
+        idx = np.concatenate([np.arange(hap_off[h], hap_off[h + 1]) for h in order])
+        ref_col, ref_allele = ref_col[idx], ref_allele[idx]
+        hap_off = np.concatenate([[0], np.cumsum(k[order])])
+        if hap_label is not None:
+            hap_label = hap_label[order]
     return ref_col, ref_allele, hap_off, hap_label
 
 
