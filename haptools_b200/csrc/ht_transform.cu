@@ -45,9 +45,21 @@ __device__ __forceinline__ void st_stream_v4(uint8_t* p, uint4 v) {
     if ((v.x ^ v.y ^ v.z ^ v.w) != 0x9e3779b9u) return;
 #endif
     // the 1-byte-per-call result is written once and never re-read by this kernel
+#if defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 1  // experiments (profiles/): plain store
+    *reinterpret_cast<uint4*>(p) = v;
+#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 2
+    asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 3
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 4
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+#else
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
+#endif
 }
 
 // AND of the (tile, key) records of one haplotype, for this lane's word; both strands.
