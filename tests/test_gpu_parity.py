@@ -418,6 +418,29 @@ def test_pgen_stream(chunk):
     np.testing.assert_array_equal(hdist.unpack_result_bits(bits, n), want)
 
 
+def test_pgen_stream_many_chunks_ring():
+    """A longer stream (24 chunks through 3 pinned host buffers and 2 device buffers) from a
+    reader that fills the buffers like pgenlib does; checked against the oracle."""
+    n, V, H = 6000, 1536, 400
+    plan = synth.synth_plan(V, H, seed=5, max_alleles=6)
+    gt = synth.synth_gt(n, V, seed=8, mode=1, missing_per_64k=300)
+    rows = gt.transpose(1, 0, 2).reshape(V, 2 * n).astype(np.int32)
+    rows[rows == 255] = -9
+    calls = []
+
+    def fill(idx, out):
+        calls.append(len(idx))
+        np.take(rows, idx, axis=0, out=out)
+
+    reader = stream.ArrayPgenReader(fill=fill, n_samples=n)
+    stats = {}
+    got = stream.transform_pgen_stream(reader, np.arange(V, dtype=np.uint32), n, plan, chunk_variants=64, stats=stats)
+    want = orc.transform_from_csr(gt, plan.key_col().astype(np.int64), plan.key_allele,
+                                  plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
+    np.testing.assert_array_equal(got, want)
+    assert stats["chunks"] == len(calls) == -(-plan.n_vars // 64) and sum(calls) == plan.n_vars
+
+
 # ------------------------------------------------------------------ host pipeline
 @pytest.mark.parametrize("lay", ["C", "F", "C3", "F3"])
 def test_host_pipeline_chunked(lay):
