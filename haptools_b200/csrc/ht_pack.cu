@@ -178,13 +178,9 @@ __device__ __forceinline__ uint4 load_chunk16(const uint8_t* p, int nvalid) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// one (tile, variant) item of the variant-major kernel; executed by a whole warp
 template <bool kAnc>
-__global__ void __launch_bounds__(kPackThreads)
-pack_vm_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = tile0 + blockIdx.x / n_vblocks;
-    const int64_t v = (int64_t)(blockIdx.x % n_vblocks) * kPackWarps + warp;
-    if (v >= a.n_vars) return;
+__device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, int64_t v, int lane) {
     const uint32_t col = __ldg(a.var_col + v);
     const uint32_t kb = __ldg(a.var_key_off + v), ke = __ldg(a.var_key_off + v + 1);
     const int rows = (int)min((int64_t)kTileSamples, a.n - tile * kTileSamples);
@@ -283,6 +279,18 @@ pack_vm_kernel(const PackArgs a, uint32_t n_vblocks, int64_t tile0) {
             }
         }
     }
+}
+
+// Grid-stride over (tile, variant) items, tile-major: a warp does only 2 KB of work per item,
+// so short-lived CTAs (one item per warp) are bound by CTA launch rate, not by memory.
+template <bool kAnc>
+__global__ void __launch_bounds__(kPackThreads)
+pack_vm_kernel(const PackArgs a, int64_t n_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_items = n_tiles * a.n_vars;
+    for (int64_t item = (int64_t)blockIdx.x * kPackWarps + warp; item < n_items;
+         item += (int64_t)gridDim.x * kPackWarps)
+        pack_vm_item<kAnc>(a, item / a.n_vars, item % a.n_vars, lane);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1097,8 +1105,15 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                 set_error("variant-major pack needs s_strand=1, s_samp=2 and 16-byte aligned rows");
                 return HT_ERR_UNSUPPORTED;
             }
-            return anc ? launch_tiled(pack_vm_kernel<true>, a, n_vblocks, 0, false, st)
-                       : launch_tiled(pack_vm_kernel<false>, a, n_vblocks, 0, false, st);
+            {
+                const int64_t n_tiles = ht_num_tiles(a.n);
+                const int64_t want = (n_tiles * a.n_vars + kPackWarps - 1) / kPackWarps;
+                const unsigned grid = (unsigned)min(want, (int64_t)148 * 8 * 4);  // a few waves of resident CTAs
+                if (anc) pack_vm_kernel<true><<<grid, kPackThreads, 0, st>>>(a, n_tiles);
+                else pack_vm_kernel<false><<<grid, kPackThreads, 0, st>>>(a, n_tiles);
+                HT_CUDA_TRY(cudaGetLastError());
+                return HT_OK;
+            }
         case HT_PACK_SAMPLE_MAJOR: {
             if (!sm_ok) {
                 set_error("sample-major pack needs s_strand=1, s_var=2, 4-byte aligned rows and col_var");
