@@ -197,6 +197,28 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this process to the CPUs next to its GPU (sysfs), so that the pinned host buffers of the
+    end-to-end leg are first-touched on the GPU's own NUMA node.  Best effort."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpulist = Path(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read_text().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{bdf}: cpus {cpulist}"
+    except Exception as e:  # sysfs not visible, no such attribute, ...
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
@@ -211,6 +233,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     engine.require_cuda()
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -350,7 +373,7 @@ def run_b200(args):
             "value": world * ne * H * 2 / dt, "unit": UNIT,
             "h2d_bytes_per_step": int(host_gt.nbytes * (2 if host_anc is not None else 1)) * world,
             "d2h_bytes_per_step": int(res.nbytes) * world,
-            "samples_per_gpu": ne, "ms": dt * 1e3,
+            "samples_per_gpu": ne, "ms": dt * 1e3, "cpu_binding_rank0": numa,
             "api": "haptools_b200.engine.transform_host (the call Haplotypes.transform makes) on pinned host arrays; "
                    "all ranks concurrently, max time over ranks",
         }
