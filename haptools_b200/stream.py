@@ -85,6 +85,8 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
         ev_pack = [None] * 2          # device buffer may be overwritten once it has been packed
         t_read = 0.0
         h2d_bytes = 0
+        timing = stats is not None
+        ev_pairs = []  # (h2d start, h2d end, pack start, pack end) CUDA events per chunk
         for k, v0 in enumerate(range(0, V, chunk)):
             v1 = min(V, v0 + chunk)
             c = v1 - v0
@@ -97,18 +99,22 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
             if ev_pack[db] is not None:
                 s_in.wait_event(ev_pack[db])
             nbytes = c * 2 * n * 4
+            e0 = s_in.record_event(torch.cuda.Event(enable_timing=True)) if timing else None
             check(lib.ht_copy2d(devbuf[db].data_ptr(), nbytes, host[hb].ctypes.data, nbytes, nbytes, 1,
                                 _cuda.HT_COPY_H2D, s_in.cuda_stream), "ht_copy2d")
             h2d_bytes += nbytes
-            ev_h2d[hb] = s_in.record_event()
+            ev_h2d[hb] = s_in.record_event(torch.cuda.Event(enable_timing=True)) if timing else s_in.record_event()
             s_cmp.wait_event(ev_h2d[hb])
+            e2 = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else None
             check(
                 lib.ht_pack_i32(devbuf[db].data_ptr(), 2 * n, n, row_in_chunk.data_ptr() + 4 * v0,
                                 dplan.var_key_off.data_ptr() + 4 * v0, dplan.key_allele.data_ptr(), c, 0,
                                 plan.n_keys, planes.data_ptr(), 0, s_cmp.cuda_stream),
                 "ht_pack_i32",
             )
-            ev_pack[db] = s_cmp.record_event()
+            ev_pack[db] = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else s_cmp.record_event()
+            if timing:
+                ev_pairs.append((e0, ev_h2d[hb], e2, ev_pack[db]))
         t_packed = time.perf_counter()
         with torch.cuda.stream(s_cmp):
             if fmt == "bits":
@@ -136,6 +142,8 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
                 cur.synchronize()
                 res = host_out.view(np.bool_)
         if stats is not None:
+            stats.update(h2d_s=sum(a.elapsed_time(b) for a, b, _, _ in ev_pairs) * 1e-3,
+                         pack_s=sum(c.elapsed_time(d) for _, _, c, d in ev_pairs) * 1e-3)
             stats.update(read_s=t_read, stream_s=t_packed - t_start, total_device_s=t_done - t_start,
                          total_s=time.perf_counter() - t_start, h2d_bytes=h2d_bytes, chunks=-(-V // chunk) if V else 0)
     return res
