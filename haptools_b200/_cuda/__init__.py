@@ -12,7 +12,7 @@ import os
 
 # HT_LIB_PATH lets experiments (profiles/) load an alternative build of the same ABI
 LIB_PATH = Path(os.environ.get("HT_LIB_PATH") or Path(__file__).resolve().parent / "libhaptools_cuda.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
 HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
@@ -36,6 +36,16 @@ class PackTables(C.Structure):
     ]
 
 
+class LocalTables(C.Structure):
+    """struct ht_local_tables (include/haptools_cuda.h); pointers are device addresses."""
+
+    _fields_ = [
+        ("n_blocks", _i64), ("dmax", _i64),
+        ("blk_hap_off", _p), ("blk_key_lo", _p), ("blk_key_cnt", _p),
+        ("s_hap_off", _p), ("s_hap_key", _p), ("hap_order", _p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/haptools_cuda.h declares
 SIGNATURES = {
     "ht_version": (_i32, []),
@@ -44,8 +54,12 @@ SIGNATURES = {
     "ht_plane_bytes": (_sz, [_i64, _i64]),
     "ht_pack_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p]),
     "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
-    "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i64, _p, _p]),
+    "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "ht_transform_bits_local": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
+    "ht_unpack_bits_u8": (_i32, [_p, _i64, _i64, _p, _i64, _p]),
+    "ht_local_workspace_bytes": (_sz, [_i64, _i64]),
+    "ht_transform_u8_local": (_i32, [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "ht_count_bits": (_i32, [_p, _i64, _i64, _p, _p]),
     "ht_synth_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _p]),
     "ht_synth_ancestry": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _u32, _u32, _p]),

@@ -21,45 +21,13 @@
 //      store.  Every store instruction writes 2 x 256 contiguous bytes.
 //
 // Roofline: HBM write of n*H*2 bytes; plane reads are L2 hits (A*256 B per tile).
-#include "ht_common.cuh"
+#include "ht_transform.cuh"
 
 namespace ht {
-
-constexpr int kHapBlock = 128;      // haplotypes per CTA
-constexpr int kHapsPerWarp = 16;    // -> 32 result bits (16 haps x 2 strands) per sample
-constexpr int kWarps = kHapBlock / kHapsPerWarp;  // 8
-constexpr int kThreads = kWarps * 32;             // 256
-constexpr int kStageKeys = 3072;    // key indices staged per CTA (12 KB, each haplotype's list
-                                    // padded to a multiple of 4); longer blocks read their
-                                    // lists straight from global memory
-constexpr int kTilesPerCta = 1;     // consecutive tiles per CTA (key lists staged once)
-constexpr int kUPitch = kTileSamples + 4;  // +4 words: the 8 warps' rows land in distinct banks
 
 __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
     // planes are re-read by every haplotype that uses the key: keep them in L1/L2
     return __ldg(p);
-}
-
-__device__ __forceinline__ void st_stream_v4(uint8_t* p, uint4 v) {
-#ifdef HT_EXP_NO_OUT_STORE  // experiment only (profiles/): keep the math alive, drop the stores
-    if ((v.x ^ v.y ^ v.z ^ v.w) != 0x9e3779b9u) return;
-#endif
-    // the 1-byte-per-call result is written once and never re-read by this kernel
-#if defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 1  // experiments (profiles/): plain store
-    *reinterpret_cast<uint4*>(p) = v;
-#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 2
-    asm volatile("st.global.wt.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 3
-    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#elif defined(HT_EXP_STORE_MODE) && HT_EXP_STORE_MODE == 4
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
-#else
-    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w)
-                 : "memory");
-#endif
 }
 
 // AND of the (tile, key) records of one haplotype, for this lane's word; both strands.
@@ -158,67 +126,15 @@ __device__ __forceinline__ void and_phase_staged(const char* __restrict__ tile_r
     }
 }
 
-// transpose32 (ht_common.cuh) with the 16- and 8-bit stages done by PRMT (2 instructions per
-// word pair instead of 5)
-__device__ __forceinline__ void transpose32_dev(uint32_t (&a)[32]) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t lo = a[k], hi = a[k + 16];
-        a[k] = __byte_perm(lo, hi, 0x5410);
-        a[k + 16] = __byte_perm(lo, hi, 0x7632);
-    }
-#pragma unroll
-    for (int k = 0; k < 32; k = (k + 8 + 1) & ~8) {
-        const uint32_t lo = a[k], hi = a[k + 8];
-        a[k] = __byte_perm(lo, hi, 0x6240);
-        a[k + 8] = __byte_perm(lo, hi, 0x7351);
-    }
-    uint32_t m = 0x0f0f0f0fu;
-#pragma unroll
-    for (int j = 4; j != 0; j >>= 1, m ^= (m << j)) {
-#pragma unroll
-        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
-            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
-            a[k] ^= (t << j);
-            a[k + j] ^= t;
-        }
-    }
-}
-
-__device__ __forceinline__ uint4 expand16(uint32_t bits) {
-    uint4 o;
-    o.x = spread4(bits & 15u);
-    o.y = spread4((bits >> 4) & 15u);
-    o.z = spread4((bits >> 8) & 15u);
-    o.w = spread4((bits >> 12) & 15u);
-    return o;
-}
-
-// out_vec: 16 -> every full 8-haplotype group is stored with one 16-byte store (requires
-//          out and out_s_samp to be multiples of 16); 2 -> 2-byte stores only (any layout
-//          with even addresses); 1 -> byte stores.
-template <int kOutVec>
-__global__ void __launch_bounds__(kThreads, 4)
-transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
-                    const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
-                    int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0,
-                    uint8_t* __restrict__ out, int64_t out_s_samp,
-                    unsigned long long* __restrict__ counts) {
-    __shared__ __align__(16) uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
-    __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
-    __shared__ uint32_t s_off[kHapBlock + 1];                  // CSR offsets of the block
-    __shared__ uint32_t s_quad[kHapBlock + 1];                 // first quad of each haplotype
-    __shared__ uint32_t s_wsum[kHapBlock / 32];
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    // a CTA handles kTilesPerCta consecutive tiles of one haplotype block: the key lists are
-    // staged once and reused
-    const int64_t tile_first = tile0 + (int64_t)(blockIdx.x / n_hap_blocks) * kTilesPerCta;
-    const int64_t n_tiles_all = (n_samples + kTileSamples - 1) / kTileSamples;
-    const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
-    const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
-
+// Stage the CSR slice of one haplotype block (offsets, then every warp the lists of its own
+// 16 haplotypes as padded, flagged quads of record byte offsets).  Called by all threads of the
+// CTA; `my_row` (the warp's exchange row) is scratch.  Returns whether the lists were staged.
+__device__ __forceinline__ bool stage_block(const uint32_t* __restrict__ hap_off,
+                                            const uint32_t* __restrict__ hap_key, int64_t h0,
+                                            int n_blk_haps, int64_t n_keys, uint32_t* s_off,
+                                            uint32_t* s_quad, uint32_t* s_wsum, uint32_t* s_keys,
+                                            uint32_t* my_row, int hl_begin, int hl_end) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- stage the block's CSR slice: offsets, then each key list padded to quads ------
     for (int i = tid; i <= n_blk_haps; i += kThreads) s_off[i] = __ldg(hap_off + h0 + i);
     __syncthreads();
@@ -242,9 +158,6 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
     if (tid == 0) s_quad[kHapBlock] = s_wsum[0] + s_wsum[1] + s_wsum[2] + s_wsum[3];
     __syncthreads();
     // n_keys == 0 means every haplotype is empty and `planes` may be NULL: never load
-    const int hl_begin = warp * kHapsPerWarp;
-    const int hl_end = min(hl_begin + kHapsPerWarp, n_blk_haps);
-    uint32_t* my_row = s_u + warp * kUPitch;
     // every warp stages (and later consumes) the lists of its own 16 haplotypes: a contiguous
     // slice of hap_key.  Raw copy first (independent coalesced loads, one round trip), into
     // the warp's exchange row, which is free until the AND phase parks results in it.
@@ -281,8 +194,67 @@ transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int6
     }
     __syncwarp();
 
+    return staged;
+}
+
+// out_vec: 16 -> every full 8-haplotype group is stored with one 16-byte store (requires
+//          out and out_s_samp to be multiples of 16); 2 -> 2-byte stores only (any layout
+//          with even addresses); 1 -> byte stores.
+template <int kOutVec>
+__global__ void __launch_bounds__(kThreads, 4)
+transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
+                    const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
+                    const uint32_t* __restrict__ quad_off16, const uint4* __restrict__ quads,
+                    int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0,
+                    uint8_t* __restrict__ out, int64_t out_s_samp,
+                    unsigned long long* __restrict__ counts) {
+    __shared__ __align__(16) uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
+    __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
+    __shared__ uint32_t s_off[kHapBlock + 1];                  // CSR offsets of the block
+    __shared__ uint32_t s_quad[kHapBlock + 1];                 // first quad of each haplotype
+    __shared__ uint32_t s_wsum[kHapBlock / 32];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    // a CTA handles kTilesPerCta consecutive tiles of one haplotype block: the key lists are
+    // staged once and reused
+    const int64_t tile_first = tile0 + (int64_t)(blockIdx.x / n_hap_blocks) * kTilesPerCta;
+    const int64_t n_tiles_all = (n_samples + kTileSamples - 1) / kTileSamples;
+    const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
+    const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
+
+    const int hl_begin = warp * kHapsPerWarp;
+    const int hl_end = min(hl_begin + kHapsPerWarp, n_blk_haps);
+    uint32_t* my_row = s_u + warp * kUPitch;
+    // n_keys == 0 means every haplotype is empty and `planes` may be NULL: never load
+    bool staged = false;
+    uint32_t q_begin = 0, q_end = 0;
+    if (quads) {
+        // the planner already laid the lists out as padded, flagged quads (plan.py quad_tables):
+        // every warp copies the quads of its own 16 haplotypes, no CTA-wide pass
+        const int64_t g0 = (h0 >> 4), n16 = (n_haps + kHapsPerWarp - 1) >> 4;
+        const uint32_t blk_q0 = __ldg(quad_off16 + g0);
+        const uint32_t blk_q1 = __ldg(quad_off16 + min(g0 + kWarps, n16));
+        if ((blk_q1 - blk_q0) * 4u <= (uint32_t)kStageKeys) {
+            staged = true;
+            if (hl_begin < hl_end) {
+                const uint32_t w_q0 = __ldg(quad_off16 + g0 + warp), w_q1 = __ldg(quad_off16 + g0 + warp + 1);
+                q_begin = w_q0 - blk_q0;
+                q_end = w_q1 - blk_q0;
+                uint4* dst = reinterpret_cast<uint4*>(s_keys);
+                for (uint32_t i = q_begin + lane; i < q_end; i += 32) dst[i] = __ldg(quads + blk_q0 + i);
+            }
+            __syncwarp();
+        }
+    }
+    if (!staged) {  // block-uniform
+        staged = stage_block(hap_off, hap_key, h0, n_blk_haps, n_keys, s_off, s_quad, s_wsum, s_keys,
+                             my_row, hl_begin, hl_end);
+        q_begin = s_quad[hl_begin];
+        q_end = s_quad[hl_end];
+    }
+
     uint2* park = reinterpret_cast<uint2*>(my_row) + lane;
-    const uint32_t q_begin = s_quad[hl_begin], q_end = s_quad[hl_end];
 
 #pragma unroll 1
     for (int ti = 0; ti < kTilesPerCta; ++ti) {
@@ -442,8 +414,9 @@ static int check_common(const uint32_t* planes, int64_t n_samples, int64_t n_key
 extern "C" {
 
 int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
-                    const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
-                    uint8_t* out, int64_t out_s_samp, uint64_t* counts, void* stream) {
+                    const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                    const uint32_t* quads, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                    uint64_t* counts, void* stream) {
     using namespace ht;
     if (int rc = check_common(planes, n_samples, n_keys, hap_off, hap_key, n_haps)) return rc;
     if (counts && n_haps > 0)
@@ -452,6 +425,11 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
     unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
     if (!out) return bad_arg("out is NULL");
     if (out_s_samp < 2 * n_haps) return bad_arg("out_s_samp < 2 * n_haps");
+    if ((quad_off16 == nullptr) != (quads == nullptr)) return bad_arg("quad_off16 and quads go together");
+    if (quads && (reinterpret_cast<uintptr_t>(quads) & 15)) return bad_arg("quads must be 16-byte aligned");
+    if (n_keys == 0 || n_keys >= kMaxStagedKeys) quads = nullptr;  // record offsets need key * 256 < 2^32
+    const uint4* quads4 = reinterpret_cast<const uint4*>(quads);
+    if (!quads4) quad_off16 = nullptr;
     // with no keys at all every haplotype is empty; the kernel then never touches `planes`
     const int64_t n_tiles = ht_num_tiles(n_samples);
     const int64_t n_hb = (n_haps + kHapBlock - 1) / kHapBlock;
@@ -470,13 +448,13 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
         const dim3 grid((unsigned)(((nt + kTilesPerCta - 1) / kTilesPerCta) * n_hb));
         cudaStream_t st = (cudaStream_t)stream;
         if (vec == 16)
-            transform_u8_kernel<16><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
+            transform_u8_kernel<16><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key, quad_off16, quads4,
                                                              n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         else if (vec == 2)
-            transform_u8_kernel<2><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
+            transform_u8_kernel<2><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key, quad_off16, quads4,
                                                             n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         else
-            transform_u8_kernel<1><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key,
+            transform_u8_kernel<1><<<grid, kThreads, 0, st>>>(planes, n_samples, n_keys, hap_off, hap_key, quad_off16, quads4,
                                                             n_haps, (uint32_t)n_hb, t0, out, out_s_samp, cnt);
         HT_CUDA_TRY(cudaGetLastError());
     }

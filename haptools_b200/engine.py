@@ -23,7 +23,7 @@ import torch
 
 from . import _cuda
 from ._cuda import HaptoolsCudaError, check
-from .plan import TransformPlan
+from .plan import TransformPlan, build_local_tables
 
 TILE = _cuda.TILE_SAMPLES
 
@@ -47,9 +47,10 @@ def _stream_ptr(stream=None) -> int:
 class DevicePlan:
     """A TransformPlan uploaded to one device (a few MB; replicated on every rank)."""
 
-    def __init__(self, plan: TransformPlan, device=None):
+    def __init__(self, plan: TransformPlan, device=None, local_dmax: int = None, local_max_block: int = None):
         require_cuda()
         self.plan = plan
+        self._local_kw = {k: v for k, v in (("dmax", local_dmax), ("max_block", local_max_block)) if v}
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
         def up(a, dtype):
@@ -62,6 +63,9 @@ class DevicePlan:
         self.key_label = up(plan.key_label, np.uint8)
         self.hap_off = up(plan.hap_off, np.int32)
         self.hap_key = up(plan.hap_key, np.int32)
+        quad_off16, quads = plan.quad_tables()
+        self.quad_off16 = up(quad_off16, np.int32)
+        self.quads = up(quads, np.int32)
         self.col_var = up(plan.col_var(), np.int32)
         col_key01, col_key_range, var_other = plan.fast_tables()
         self.col_key01 = up(col_key01, np.int32)
@@ -73,9 +77,29 @@ class DevicePlan:
             _ptr(self.col_key_range), _ptr(self.var_other) if len(var_other) else None, len(var_other),
         )
 
+        self._local = None  # (LocalTables, device tensors, ctypes struct), built on first use
+        self._up = up
+
     n_haps = property(lambda self: self.plan.n_haps)
     n_keys = property(lambda self: self.plan.n_keys)
     n_vars = property(lambda self: self.plan.n_vars)
+
+    def local(self):
+        """Locality tables of the two-phase transform (plan.build_local_tables), uploaded once:
+        returns (LocalTables, _cuda.LocalTables)."""
+        if self._local is None:
+            lt = build_local_tables(self.plan, **self._local_kw)
+            dev = [self._up(a, np.int32) for a in
+                   (lt.blk_hap_off, lt.blk_key_lo, lt.blk_key_cnt, lt.s_hap_off, lt.s_hap_key, lt.order)]
+            struct = _cuda.LocalTables(lt.n_blocks, lt.dmax, *[_ptr(t) if t.numel() else None for t in dev])
+            self._local = (lt, dev, struct)
+        return self._local[0], self._local[2]
+
+    def use_local(self) -> bool:
+        """Does the two-phase transform move fewer bytes through L2 than the one-kernel form?"""
+        if self.plan.n_haps == 0 or self.plan.n_refs < 4 * self.plan.n_haps:
+            return False  # cannot pay for the packed intermediate: skip building the tables
+        return self.local()[0].worthwhile(self.plan.n_refs)
 
 
 def plane_bytes(n_samples: int, n_keys: int) -> int:
@@ -107,13 +131,47 @@ def pack(dplan: DevicePlan, gt_ptr: int, gt_strides, n_samples: int, planes: tor
     )
 
 
+def local_workspace(dplan: DevicePlan, n_samples: int, device) -> torch.Tensor:
+    """Scratch of the two-phase transform: the bit-packed result of one group of tiles."""
+    nbytes = int(_cuda.lib().ht_local_workspace_bytes(n_samples, dplan.n_haps))
+    return torch.empty(max(nbytes, 16) // 4, dtype=torch.int32, device=device)
+
+
 def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_ptr: int, pitch: int,
-                 stream=None, counts: torch.Tensor = None) -> None:
+                 stream=None, counts: torch.Tensor = None, method: str = "auto",
+                 workspace: torch.Tensor = None, use_quads: bool = True) -> None:
     """K2 on raw device pointers.  `counts` (optional int64[H] tensor) receives the number of
-    present copies of every haplotype (the numerator of check_maf)."""
+    present copies of every haplotype (the numerator of check_maf).
+
+    method  "direct": one kernel, one L2 record read per haplotype allele (ht_transform_u8);
+            "local": two phases through shared memory and a bit-packed intermediate
+            (ht_transform_u8_local); "auto": whichever moves fewer bytes through L2 for this
+            plan (DevicePlan.use_local).  Results are identical.
+    use_quads  False: let the kernel build its padded key quads from the CSR itself (the form
+            without planner support; kept for callers that only have hap_off / hap_key)."""
+    if method not in ("auto", "direct", "local"):
+        raise ValueError("method must be 'auto', 'direct' or 'local'")
+    if method == "local" or (method == "auto" and dplan.use_local()):
+        if dplan.n_haps == 0 or n_samples == 0:
+            return
+        _, tables = dplan.local()
+        if workspace is None:
+            # allocated on the launching stream: the caching allocator then reuses the block
+            # only in that stream's order
+            with torch.cuda.stream(stream or torch.cuda.current_stream(dplan.device)):
+                workspace = local_workspace(dplan, n_samples, dplan.device)
+        check(
+            _cuda.lib().ht_transform_u8_local(
+                _ptr(planes), n_samples, dplan.n_keys, ctypes.byref(tables), dplan.n_haps, out_ptr, pitch,
+                _ptr(counts), _ptr(workspace), workspace.numel() * workspace.element_size(), _stream_ptr(stream),
+            ),
+            "ht_transform_u8_local",
+        )
+        return
     check(
         _cuda.lib().ht_transform_u8(
             _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
+            _ptr(dplan.quad_off16) if use_quads else None, _ptr(dplan.quads) if use_quads else None,
             dplan.n_haps, out_ptr, pitch, _ptr(counts), _stream_ptr(stream),
         ),
         "ht_transform_u8",
@@ -121,7 +179,22 @@ def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_pt
 
 
 def transform_bits(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_bits: torch.Tensor,
-                   stream=None) -> None:
+                   stream=None, method: str = "auto", counts: torch.Tensor = None) -> None:
+    """Bit-packed result (tiles, H, 32, 2); `method` as in transform_u8 (`counts` needs "local")."""
+    if method == "local" or (method == "auto" and dplan.n_haps and dplan.use_local()):
+        if dplan.n_haps == 0 or n_samples == 0:
+            return
+        _, tables = dplan.local()
+        check(
+            _cuda.lib().ht_transform_bits_local(
+                _ptr(planes), n_samples, dplan.n_keys, ctypes.byref(tables), dplan.n_haps, _ptr(out_bits),
+                _ptr(counts), _stream_ptr(stream),
+            ),
+            "ht_transform_bits_local",
+        )
+        return
+    if counts is not None:
+        raise ValueError("counts are only produced by the local form; use count_bits")
     check(
         _cuda.lib().ht_transform_bits(
             _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
@@ -129,6 +202,11 @@ def transform_bits(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_
         ),
         "ht_transform_bits",
     )
+
+
+def unpack_bits_u8(bits: torch.Tensor, n_samples: int, n_haps: int, out_ptr: int, pitch: int, stream=None) -> None:
+    """Bit-packed result -> (n, H, 2) bytes (ht_unpack_bits_u8)."""
+    check(_cuda.lib().ht_unpack_bits_u8(_ptr(bits), n_samples, n_haps, out_ptr, pitch, _stream_ptr(stream)), "ht_unpack_bits_u8")
 
 
 def count_bits(bits: torch.Tensor, n_samples: int, n_haps: int, stream=None) -> torch.Tensor:

@@ -101,6 +101,36 @@ class TransformPlan:
             return np.full((self.n_cols, 2), -1, dtype=np.int32), np.arange(self.n_vars, dtype=np.uint32)
         return k01, other
 
+    def quad_tables(self):
+        """
+        The key lists in the form the transform kernel walks them (csrc/ht_transform.cu): every
+        list padded to whole quads of 4 by repeating its last key (AND is idempotent), entries
+        are BYTE offsets of the (tile, key) record inside a tile (key * 256), and the low bits of
+        the first entry of a quad carry flags: 1 = last quad of its haplotype, 2 = haplotype
+        without alleles (one all-zero quad).  Returns (quad_off16, quads):
+          quad_off16  (ceil(H/16) + 1,) uint32: first quad of every group of 16 haplotypes (the
+                      unit one warp processes)
+          quads       (Q, 4) uint32
+        or (None, None) when a record offset does not fit 32 bits (>= 2^24 keys).
+        """
+        if self.n_keys >= (1 << 24) or self.n_haps == 0:
+            return None, None
+        H = self.n_haps
+        off = self.hap_off.astype(np.int64)
+        lens = np.diff(off)
+        padded = np.maximum(4, (lens + 3) & ~3)
+        qoff = np.concatenate([[0], np.cumsum(padded)])
+        hap_of = np.repeat(np.arange(H), padded)
+        j = np.arange(qoff[-1]) - qoff[hap_of]
+        ln = lens[hap_of]
+        src = off[hap_of] + np.minimum(j, np.maximum(ln - 1, 0))
+        key = self.hap_key.astype(np.int64)
+        val = np.where(ln > 0, key[np.minimum(src, max(len(key) - 1, 0))] << 8, 0) if len(key) else np.zeros(len(j), np.int64)
+        first = (j & 3) == 0
+        val = val | np.where(first & (j + 4 >= padded[hap_of]), 1, 0) | np.where(first & (ln == 0), 2, 0)
+        quad_off16 = (qoff[np.minimum(np.arange(0, H + 16, 16), H)] // 4)[: (H + 15) // 16 + 1]
+        return quad_off16.astype(np.uint32), val.astype(np.uint32).reshape(-1, 4)
+
     def key_col(self) -> np.ndarray:
         """Column of each key, (A,) uint32."""
         return np.repeat(self.var_col, np.diff(self.var_key_off.astype(np.int64)))
@@ -232,3 +262,110 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
     ref_label = np.repeat(ancestries.astype(np.int64), lens) if ancestry else None
     plan = plan_from_refs(cols[flat], allele_arr[flat], hap_off, gts.data.shape[1], ref_label)
     return (plan, never) if unknown_label == "never" else plan
+
+
+# ----------------------------------------------------------------------------------------
+# locality tables of the two-phase ("local") transform
+# ----------------------------------------------------------------------------------------
+@dataclass
+class LocalTables:
+    """
+    Haplotypes re-ordered by the position of their first key and cut into blocks whose keys
+    fall into a short contiguous key range (keys are numbered by variant column, so a block of
+    neighbouring haplotypes touches a contiguous run of (tile, key) records).  The local
+    transform stages that run in shared memory once per (tile, block) instead of reading one
+    256-byte record from L2 per haplotype allele, writes the bit-packed result in this order
+    and a second kernel unpacks it into the caller's haplotype order (ht_transform_u8_local).
+
+    order[j]        haplotype (caller's index) at sorted position j
+    pos[h]          sorted position of haplotype h (inverse of order)
+    blk_hap_off     (NB+1,) sorted positions: block b holds positions blk_hap_off[b]..[b+1]-1
+    blk_key_lo      (NB,)   first key of the block's range
+    blk_key_cnt     (NB,)   number of keys in the range; 0 = not staged (the block's haplotype
+                    lists then hold global key numbers)
+    s_hap_off       (H+1,)  CSR offsets in sorted order
+    s_hap_key       (K,)    keys in sorted order, RELATIVE to blk_key_lo for staged blocks
+    """
+
+    dmax: int
+    order: np.ndarray
+    pos: np.ndarray
+    blk_hap_off: np.ndarray
+    blk_key_lo: np.ndarray
+    blk_key_cnt: np.ndarray
+    s_hap_off: np.ndarray
+    s_hap_key: np.ndarray
+    staged_reads: int  # (tile, key) records read per tile by phase 1
+
+    @property
+    def n_blocks(self) -> int:
+        return len(self.blk_key_lo)
+
+    def worthwhile(self, n_refs: int) -> bool:
+        """Fewer L2 accesses than the one-kernel transform?  Per tile, in 256-byte records: the
+        direct kernel reads one record per haplotype allele (n_refs); the local path reads
+        `staged_reads` and moves the packed result four times (written, evicted, re-read)."""
+        n_haps = len(self.order)
+        return self.staged_reads + 4 * n_haps < 0.9 * n_refs
+
+
+LOCAL_DMAX = 288  # records staged per block: 72 KB of shared memory, 3 CTAs per SM
+LOCAL_MAX_BLOCK = 128  # haplotypes per block at most
+
+
+def build_local_tables(plan: TransformPlan, dmax: int = LOCAL_DMAX, max_block: int = LOCAL_MAX_BLOCK) -> LocalTables:
+    H, K = plan.n_haps, plan.n_refs
+    off = plan.hap_off.astype(np.int64)
+    key = plan.hap_key.astype(np.int64)
+    lens = np.diff(off)
+    nonempty = lens > 0
+    mn = np.full(H, -1, dtype=np.int64)
+    mx = np.full(H, -1, dtype=np.int64)
+    if K:
+        starts = off[:-1][nonempty]  # consecutive non-empty starts delimit exactly the lists
+        mn[nonempty] = np.minimum.reduceat(key, starts)
+        mx[nonempty] = np.maximum.reduceat(key, starts)
+    order = np.argsort(mn, kind="stable")
+    pos = np.empty(H, dtype=np.int64)
+    pos[order] = np.arange(H)
+    s_lens = lens[order]
+    s_off = np.concatenate([[0], np.cumsum(s_lens)]).astype(np.int64)
+    # gather the key lists in sorted order
+    src = np.repeat(off[:-1][order] - s_off[:-1], s_lens) + np.arange(K)
+    s_key = key[src]
+    smn, smx = mn[order], mx[order]
+    blk_off, blk_lo, blk_cnt = [0], [], []
+    staged_reads = 0
+    j = 0
+    while j < H:
+        e = min(H, j + max_block)
+        cm = np.maximum.accumulate(smx[j:e])
+        if cm[-1] < 0:  # only haplotypes without alleles
+            take, lo, cnt = e - j, 0, 0
+        else:
+            first = int(np.argmax(smn[j:e] >= 0))
+            lo = int(smn[j + first])
+            take = int(np.searchsorted(cm, lo + dmax, side="left"))  # cm - lo + 1 <= dmax
+            if take <= first:  # the first haplotype with alleles alone is wider than dmax
+                take, cnt = first + 1, 0
+                staged_reads += int(s_lens[j + first])
+            else:
+                cnt = int(cm[take - 1]) - lo + 1
+                staged_reads += cnt
+        blk_lo.append(lo)
+        blk_cnt.append(cnt)
+        j += take
+        blk_off.append(j)
+    blk_off = np.asarray(blk_off, dtype=np.int64)
+    blk_lo = np.asarray(blk_lo, dtype=np.int64)
+    blk_cnt = np.asarray(blk_cnt, dtype=np.int64)
+    # relative keys for staged blocks
+    blk_of_hap = np.repeat(np.arange(len(blk_lo)), np.diff(blk_off))
+    sub = np.where(blk_cnt > 0, blk_lo, 0)[blk_of_hap]
+    s_key = s_key - np.repeat(sub, s_lens)
+    return LocalTables(
+        dmax=int(dmax), order=order.astype(np.uint32), pos=pos.astype(np.uint32),
+        blk_hap_off=blk_off.astype(np.uint32), blk_key_lo=blk_lo.astype(np.uint32),
+        blk_key_cnt=blk_cnt.astype(np.uint32), s_hap_off=s_off.astype(np.uint32),
+        s_hap_key=s_key.astype(np.uint32), staged_reads=int(staged_reads),
+    )

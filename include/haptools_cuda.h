@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define HT_ABI_VERSION 6
+#define HT_ABI_VERSION 7
 
 #define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
 #define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
@@ -167,6 +167,13 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
  * with ancestry folded into the keys also transform.py:144-148).
  *
  *   hap_off[H+1], hap_key[K]  CSR of key indices per haplotype (`idxs`, haplotypes.py:1380).
+ *   quad_off16[ceil(H/16)+1], quads[4*Q]  optional (both NULL or both given; `quads` 16-byte
+ *           aligned): the same lists as the kernel walks them -- every list padded to whole
+ *           quads of 4 by repeating its last key, entries = key * 256 (byte offset of the record
+ *           inside a tile), low bits of a quad's first entry = flags (1: last quad of its
+ *           haplotype, 2: haplotype without alleles), quad_off16[g] = first quad of haplotypes
+ *           16 g .. 16 g + 15 (haptools_b200/plan.py quad_tables).  Without them the kernel
+ *           builds the quads from the CSR in every CTA (15-20 % slower at UKB scale).
  *   out     uint8 matrix: element (s, h, c) at out + s*out_s_samp + 2*h + c receives exactly
  *           0x00 or 0x01 (numpy bool bytes).  A haplotype without keys yields 0x01
  *           (np.all over an empty axis).  out_s_samp >= 2*H.  Rows >= n_samples are not
@@ -177,8 +184,9 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
  *           second pass over the result; here they fall out of the kernel (popcount).
  */
 int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
-                    const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
-                    uint8_t* out, int64_t out_s_samp, uint64_t* counts, void* stream);
+                    const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                    const uint32_t* quads, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                    uint64_t* counts, void* stream);
 
 /*
  * K2, bit-packed result: out_bits has the plane layout with haplotypes in place of keys
@@ -189,6 +197,53 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
 int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                       const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
                       uint32_t* out_bits, void* stream);
+
+/*
+ * K2, two-phase ("local") form: same results as ht_transform_u8 / ht_transform_bits with fewer
+ * L2 accesses when haplotypes share alleles (K >> A).  The planner orders the haplotypes by
+ * their first key and cuts them into blocks whose keys fall into a run of at most `dmax`
+ * consecutive keys (haptools_b200/plan.py build_local_tables); phase 1 stages that run of
+ * (tile, key) records in shared memory with one TMA bulk copy per (tile, block), ANDs every
+ * haplotype of the block out of shared memory and writes the bit-packed result; phase 2
+ * (ht_unpack_bits_u8) expands it to bytes.  All tables are DEVICE pointers:
+ *   blk_hap_off[NB+1]  block b holds the haplotypes at sorted positions blk_hap_off[b] ..
+ *                      blk_hap_off[b+1]-1 (at most 128 per block)
+ *   blk_key_lo[NB], blk_key_cnt[NB]  the block's run of keys; cnt == 0: not staged (records are
+ *                      read straight from the plane workspace), cnt <= dmax otherwise
+ *   s_hap_off[H+1], s_hap_key[K]  CSR of the key lists in sorted order; keys of a staged block
+ *                      are RELATIVE to blk_key_lo (< cnt), keys of other blocks absolute
+ *   hap_order[H]       caller's index of the haplotype at each sorted position
+ */
+typedef struct ht_local_tables {
+    int64_t n_blocks;
+    int64_t dmax;
+    const uint32_t* blk_hap_off;
+    const uint32_t* blk_key_lo;
+    const uint32_t* blk_key_cnt;
+    const uint32_t* s_hap_off;
+    const uint32_t* s_hap_key;
+    const uint32_t* hap_order;
+} ht_local_tables;
+
+/* Phase 1 alone: the bit-packed result of ht_transform_bits (same layout, caller's haplotype
+ * order), plus the optional allele counts of ht_transform_u8. */
+int ht_transform_bits_local(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                            const ht_local_tables* tables, int64_t n_haps, uint32_t* out_bits,
+                            uint64_t* counts, void* stream);
+
+/* Phase 2 alone: bit-packed result (tiles, H, 32, 2) -> bytes; element (s, h, c) at
+ * out + s*out_s_samp + 2*h + c receives 0x00 / 0x01.  Rows >= n_samples are not touched. */
+int ht_unpack_bits_u8(const uint32_t* bits, int64_t n_samples, int64_t n_haps, uint8_t* out,
+                      int64_t out_s_samp, void* stream);
+
+/* Both phases, alternating over groups of tiles through a caller-provided workspace of
+ * `workspace_bytes` (16-byte aligned, at least n_haps * 256 bytes = one tile;
+ * ht_local_workspace_bytes() is the recommended size).  Arguments as ht_transform_u8. */
+size_t ht_local_workspace_bytes(int64_t n_samples, int64_t n_haps);
+int ht_transform_u8_local(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                          const ht_local_tables* tables, int64_t n_haps, uint8_t* out,
+                          int64_t out_s_samp, uint64_t* counts, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /*
  * Per-haplotype allele counts of a bit-packed result (popcount over samples and strands)

@@ -58,7 +58,7 @@ def test_size_helpers(lib):
 
 def test_argument_errors_do_not_need_a_gpu(lib):
     # argument validation happens before any CUDA call
-    rc = lib.ht_transform_u8(None, -1, 0, None, None, 0, None, 0, None, None)
+    rc = lib.ht_transform_u8(None, -1, 0, None, None, None, None, 0, None, 0, None, None)
     assert rc == _cuda.HT_ERR_BAD_ARG and b"negative" in lib.ht_last_error()
     with pytest.raises(ValueError):
         _cuda.check(rc, "ht_transform_u8")

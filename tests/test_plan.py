@@ -153,3 +153,41 @@ def test_synth_numpy_properties():
     _check_plan(plan)
     k = np.diff(plan.hap_off.astype(np.int64))
     assert k.min() >= 2 and k.max() <= 20
+
+
+def test_quad_tables_restate_the_lists():
+    """plan.quad_tables: padded, flagged quads of record byte offsets, one offset per 16 haplotypes."""
+    import numpy as np
+    from haptools_b200.plan import plan_from_refs
+
+    rng = np.random.default_rng(4)
+    H, p = 70, 40
+    k = rng.integers(0, 11, size=H)
+    k[3] = 0
+    off = np.concatenate([[0], np.cumsum(k)])
+    cols = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, np.int64)])
+    plan = plan_from_refs(cols, rng.integers(0, 2, size=len(cols)), off, p)
+    q16, quads = plan.quad_tables()
+    assert q16.dtype == np.uint32 and quads.dtype == np.uint32 and quads.shape[1] == 4
+    assert len(q16) == (H + 15) // 16 + 1 and q16[0] == 0 and q16[-1] == len(quads)
+    qi = 0
+    for h in range(H):
+        keys = plan.hap_key[plan.hap_off[h]:plan.hap_off[h + 1]].astype(np.int64)
+        nq = max(1, (len(keys) + 3) // 4)
+        if h % 16 == 0:
+            assert q16[h // 16] == qi
+        flat = quads[qi:qi + nq].astype(np.int64)
+        flags = flat[:, 0] & 0xFF
+        assert np.all(flat[:, 1:] & 0xFF == 0)
+        assert list(flags & 1) == [0] * (nq - 1) + [1]
+        assert np.all((flags & 2) == (2 if len(keys) == 0 else 0))
+        got = (flat >> 8).reshape(-1)
+        if len(keys):
+            np.testing.assert_array_equal(got[:len(keys)], keys)
+            assert np.all(got[len(keys):] == keys[-1])
+        else:
+            assert np.all(got == 0)
+        qi += nq
+    assert qi == len(quads)
+    empty = plan_from_refs(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(1, np.int64), p)
+    assert empty.quad_tables() == (None, None)
