@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--sorted-haps", action="store_true",
                     help="order the synthetic haplotypes by position, as .hap files are after `haptools index` "
                          "(default: generation order, SURVEY.md 8d)")
+    ap.add_argument("--method", default="auto", choices=["auto", "direct", "local"],
+                    help="transform form (engine.transform_u8): one kernel, two-phase local, or the engine's choice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -154,47 +156,86 @@ def run_reference(args):
 # clocks
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML poller
+    (no start-up delay, 20 ms period; the main thread sits in cudaStreamSynchronize without the
+    GIL meanwhile), `nvidia-smi -lms` as the fallback.  Samples carry a host timestamp and
+    stop(t0, t1) keeps those inside the timed window."""
+
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.how = index, [], None, None
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {
+                "hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap,
+            }
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.perf_counter(), mhz, [k for k, b in bits.items() if mask & b]))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.02)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for nm, val in zip(names, r[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
+                self.max_mhz = float(r[1])
+                self.rows.append((time.perf_counter(), float(r[0]),
+                                  [nm for nm, val in zip(self.NAMES, r[2:6]) if val.lower().startswith("active")]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self, t0=None, t1=None):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if not self.how:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        reasons = sorted({x for r in rows for x in r[2]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": reasons, "samples": len(rows),
+                "source": self.how + ", sampled inside the timed region"}
 
 
 def bind_to_gpu_numa_node(local_rank: int) -> str:
@@ -280,37 +321,42 @@ def run_b200(args):
     anc_ptr = anc.data_ptr() if anc is not None else 0
     anc_strides = anc.stride() if anc is not None else (0, 0, 0)
 
+    two_phase = args.method == "local" or (args.method == "auto" and dplan.use_local())
+    workspace = engine.local_workspace(dplan, n, dev) if two_phase else None
+    method = "local" if two_phase else "direct"
+
     def step():
         engine.pack(dplan, gt.data_ptr(), gt.stride(), n, planes, anc_ptr, anc_strides)
-        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch)
+        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch, method=method, workspace=workspace)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching (current) stream ----------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    host_t0 = time.perf_counter()
     t_begin.record()
     for k in range(K):
         ev[k][0].record()
         engine.pack(dplan, gt.data_ptr(), gt.stride(), n, planes, anc_ptr, anc_strides)
         ev[k][1].record()
-        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch)
+        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch, method=method, workspace=workspace)
         ev[k][2].record()
     t_end.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(host_t0, time.perf_counter()) if rank == 0 else None
     total_ms = t_begin.elapsed_time(t_end)
     pack_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     tr_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
@@ -346,7 +392,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         ne = min(args.e2e_samples, n)
-        del out, planes
+        del out, planes, workspace
         torch.cuda.empty_cache()
         host_gt = engine.pinned_empty((ne, p, 2))
         host_gt[:] = synth.synth_gt(min(ne, 256), p, w["seed"] + 1, mode=1, sample_offset=sample_offset)[np.arange(ne) % min(ne, 256)]
@@ -394,7 +440,7 @@ def run_b200(args):
     tr_gbs = ab["transform"] / (tr_ms * 1e-3) / 1e9
     pack_gbs = ab["pack"] / (pack_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "transform_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "transform_u8_kernel" if not two_phase else "and_local_bits_kernel + unpack_bits_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
         "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.064), "peak_source": peak_src,
         "traffic_source": "ncu --set full (profiles/r1): dram read+write per launch = 1.064 x algorithmic bytes at 131,072 samples, scaled linearly to this launch",
         "algorithmic_bytes_per_launch": ab["transform"], "ms_per_launch": tr_ms,
@@ -417,13 +463,13 @@ def run_b200(args):
         "config": {
             "workload": w["name"], "samples_per_gpu": n, "variants": p, "haplotypes": H,
             **({"samples_per_gpu_requested": n_requested, "note": "shard shrunk: the requested one did not fit in HBM"} if n != n_requested else {}),
-            "haplotype_alleles": plan.n_refs, "distinct_keys": plan.n_keys, "layout": w["layout"],
+            "haplotype_alleles": plan.n_refs, "distinct_keys": plan.n_keys, "layout": w["layout"], "transform_form": method,
             "haplotype_order": "position-sorted" if w["sort"] else "generation order (unsorted)",
             "genotypes": "blocky founders (16 per 64-variant block), device-generated from a counter hash",
             "l2": "inputs (%.1f GB) larger than L2, no flush needed" % (ab["gt"] / 1e9),
             "sharding": "samples, one shard per GPU, no collective on the path",
         },
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * K, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (1 + (2 * -(-((n + 1023) // 1024) // 64) if two_phase else 1)) * K, "clocks": clocks,
         "verified_against_oracle": verified, "ones_fraction": ones_fraction,
     }
     print(json.dumps(line), flush=True)

@@ -27,7 +27,21 @@ namespace ht {
 
 __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
     // planes are re-read by every haplotype that uses the key: keep them in L1/L2
+#if defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 1  // experiments (profiles/)
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#elif defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 2
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#elif defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 3
+    uint2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#else
     return __ldg(p);
+#endif
 }
 
 // AND of the (tile, key) records of one haplotype, for this lane's word; both strands.
@@ -60,9 +74,17 @@ constexpr uint32_t kQuadSkip = 2u;  // stands for a haplotype without alleles
 constexpr uint32_t kOffMask = 0xffffff00u;
 constexpr int64_t kMaxStagedKeys = 1 << 24;
 
-struct Batch {  // two quads = 8 plane records in flight
-    uint2 v[8];
-    uint32_t f0, f1;  // flag words of the two quads
+#ifndef HT_BATCH_QUADS
+#define HT_BATCH_QUADS 2
+#endif
+#ifndef HT_MIN_CTAS
+#define HT_MIN_CTAS 4
+#endif
+constexpr int kBQ = HT_BATCH_QUADS;  // quads per batch: 4 * kBQ plane records in flight per batch
+
+struct Batch {
+    uint2 v[4 * kBQ];
+    uint32_t f[kBQ];  // flag words of the quads
 };
 
 __device__ __forceinline__ uint2 ld_rec(const char* tile_bytes, uint32_t off) {
@@ -72,17 +94,17 @@ __device__ __forceinline__ uint2 ld_rec(const char* tile_bytes, uint32_t off) {
 __device__ __forceinline__ void load_batch(const char* __restrict__ tile_bytes,
                                            const uint4* __restrict__ quads, uint32_t q,
                                            uint32_t q_last, Batch& b) {
-    const uint4 ka = quads[q], kb = quads[min(q + 1, q_last)];
-    b.f0 = ka.x;
-    b.f1 = kb.x;
-    b.v[0] = ld_rec(tile_bytes, ka.x & kOffMask);
-    b.v[1] = ld_rec(tile_bytes, ka.y);
-    b.v[2] = ld_rec(tile_bytes, ka.z);
-    b.v[3] = ld_rec(tile_bytes, ka.w);
-    b.v[4] = ld_rec(tile_bytes, kb.x & kOffMask);
-    b.v[5] = ld_rec(tile_bytes, kb.y);
-    b.v[6] = ld_rec(tile_bytes, kb.z);
-    b.v[7] = ld_rec(tile_bytes, kb.w);
+    uint4 k[kBQ];
+#pragma unroll
+    for (int i = 0; i < kBQ; ++i) k[i] = quads[min(q + i, q_last)];
+#pragma unroll
+    for (int i = 0; i < kBQ; ++i) {
+        b.f[i] = k[i].x;
+        b.v[4 * i + 0] = ld_rec(tile_bytes, k[i].x & kOffMask);
+        b.v[4 * i + 1] = ld_rec(tile_bytes, k[i].y);
+        b.v[4 * i + 2] = ld_rec(tile_bytes, k[i].z);
+        b.v[4 * i + 3] = ld_rec(tile_bytes, k[i].w);
+    }
 }
 
 __device__ __forceinline__ void consume_quad(const uint2* v, uint32_t flags, uint32_t& r0,
@@ -113,15 +135,17 @@ __device__ __forceinline__ void and_phase_staged(const char* __restrict__ tile_r
     load_batch(tile_rec, quads, q, q_last, A);
 #pragma unroll 1
     while (true) {
-        if (q + 2 < q_end) load_batch(tile_rec, quads, q + 2, q_last, B);
-        consume_quad(A.v, A.f0, r0, r1, park);
-        if (q + 1 < q_end) consume_quad(A.v + 4, A.f1, r0, r1, park);
-        q += 2;
+        if (q + kBQ < q_end) load_batch(tile_rec, quads, q + kBQ, q_last, B);
+#pragma unroll
+        for (int i = 0; i < kBQ; ++i)
+            if (i == 0 || q + i < q_end) consume_quad(A.v + 4 * i, A.f[i], r0, r1, park);
+        q += kBQ;
         if (q >= q_end) break;
-        if (q + 2 < q_end) load_batch(tile_rec, quads, q + 2, q_last, A);
-        consume_quad(B.v, B.f0, r0, r1, park);
-        if (q + 1 < q_end) consume_quad(B.v + 4, B.f1, r0, r1, park);
-        q += 2;
+        if (q + kBQ < q_end) load_batch(tile_rec, quads, q + kBQ, q_last, A);
+#pragma unroll
+        for (int i = 0; i < kBQ; ++i)
+            if (i == 0 || q + i < q_end) consume_quad(B.v + 4 * i, B.f[i], r0, r1, park);
+        q += kBQ;
         if (q >= q_end) break;
     }
 }
@@ -201,7 +225,7 @@ __device__ __forceinline__ bool stage_block(const uint32_t* __restrict__ hap_off
 //          out and out_s_samp to be multiples of 16); 2 -> 2-byte stores only (any layout
 //          with even addresses); 1 -> byte stores.
 template <int kOutVec>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, HT_MIN_CTAS)
 transform_u8_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                     const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
                     const uint32_t* __restrict__ quad_off16, const uint4* __restrict__ quads,

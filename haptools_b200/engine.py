@@ -26,6 +26,10 @@ from ._cuda import HaptoolsCudaError, check
 from .plan import TransformPlan, build_local_tables
 
 TILE = _cuda.TILE_SAMPLES
+# The two-phase ("local") transform is bit-exact and tested, but as measured on B200 (DESIGN.md
+# section 5) it does not beat the one-kernel form yet (12.7 vs 10.1 ms on the UKB-scale plan at
+# 200 k samples): method="auto" keeps to the one-kernel form unless this is switched on.
+LOCAL_AUTO = False
 
 
 def require_cuda() -> None:
@@ -96,7 +100,10 @@ class DevicePlan:
         return self._local[0], self._local[2]
 
     def use_local(self) -> bool:
-        """Does the two-phase transform move fewer bytes through L2 than the one-kernel form?"""
+        """Should "auto" pick the two-phase transform?  Only when it is enabled (LOCAL_AUTO) and
+        the plan shares enough alleles between neighbouring haplotypes (LocalTables.worthwhile)."""
+        if not LOCAL_AUTO:
+            return False
         if self.plan.n_haps == 0 or self.plan.n_refs < 4 * self.plan.n_haps:
             return False  # cannot pay for the packed intermediate: skip building the tables
         return self.local()[0].worthwhile(self.plan.n_refs)

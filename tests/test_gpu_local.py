@@ -55,7 +55,7 @@ def test_local_random_vs_oracle(n, p, H):
         np.testing.assert_array_equal(counts.cpu().numpy(), want.sum(axis=(0, 2)))
 
 
-def test_local_structured_plan_blocks_groups_and_pitches():
+def test_local_structured_plan_blocks_groups_and_pitches(monkeypatch):
     """A plan with real locality (many haplotypes per variant), several dmax / block sizes,
     workspaces of 1 and 2 tiles (group loop), odd pitches (2-byte and 1-byte store paths)."""
     n, p, H = 3300, 700, 1500
@@ -74,6 +74,8 @@ def test_local_structured_plan_blocks_groups_and_pitches():
             np.testing.assert_array_equal(_u8(dplan, planes, n, "local", workspace=ws), want)
         np.testing.assert_array_equal(_u8(dplan, planes, n, "local", pitch=2 * H + 2), want)
         np.testing.assert_array_equal(_u8(dplan, planes, n, "local", pitch=2 * H + 3, offset=1), want)
+    assert not engine.DevicePlan(plan).use_local()  # switched off by default (engine.LOCAL_AUTO)
+    monkeypatch.setattr(engine, "LOCAL_AUTO", True)
     assert engine.DevicePlan(plan).use_local()
     np.testing.assert_array_equal(_u8(engine.DevicePlan(plan), planes, n, "auto"), want)
     with pytest.raises(ValueError):
@@ -164,7 +166,7 @@ def test_local_equals_direct_at_scale():
     n, p, H = 40_000, 5_000, 10_000
     plan = synth.synth_plan(p, H, seed=2)
     dplan = engine.DevicePlan(plan)
-    assert dplan.use_local()
+    assert dplan.local()[0].worthwhile(plan.n_refs)
     gt = torch.empty((n, p, 2), dtype=torch.uint8, device="cuda")
     _cuda.check(_cuda.lib().ht_synth_gt(gt.data_ptr(), *gt.stride(), n, p, 0, 3, 1, 20, 0), "synth")
     planes = engine.alloc_planes(n, plan.n_keys, gt.device)
