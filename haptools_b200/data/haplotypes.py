@@ -122,10 +122,13 @@ class Haplotypes:
         if hap_gts is None:
             hap_gts = GenotypesVCF(fname=None, log=self.log)
         hap_gts.samples = gts.samples
-        hap_gts.variants = np.array(
-            [(hap.id, hap.chrom, hap.start, ("A", "T")) for hap in haps],
-            dtype=hap_gts.variants.dtype,
-        )
+        # haptools/data/haplotypes.py:1369-1372, column by column instead of a tuple per haplotype
+        variants = np.empty(len(haps), dtype=hap_gts.variants.dtype)
+        variants["id"] = [hap.id for hap in haps]
+        variants["chrom"] = [hap.chrom for hap in haps]
+        variants["pos"] = [hap.start for hap in haps]
+        variants["alleles"].fill(("A", "T"))
+        hap_gts.variants = variants
         plan = plan_from_haplotypes(haps, gts, ancestry=ancestry)
         self.log.debug(f"Packing genotypes for {plan.n_keys} distinct alleles")
         if ancestry and gts.data.shape[2] != 2:

@@ -204,9 +204,12 @@ def _variant_columns(gts, var_ids: Sequence[str], who: str) -> list:
     return [var_idx[v] for v in var_ids]
 
 
-def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str = None,
+def plan_from_haplotypes_loop(haps: Sequence, gts, ancestry: bool = False, who: str = None,
                          unknown_label: str = "raise"):
     """
+    The literal, per-allele Python loop of the reference (kept as the cross-check of the
+    vectorised plan_from_haplotypes below; tests/test_plan.py compares the two).
+
     ``haps``: Haplotype objects (``.variants`` of objects with ``.id``/``.allele``; with
     ``ancestry=True`` also ``.ancestry``); ``gts``: a GenotypesVCF-like object with
     ``.data``, a structured ``.variants`` (``id``, ``alleles``) and, with ``ancestry=True``,
@@ -261,6 +264,84 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
     cols = np.asarray(cols, dtype=np.int64).reshape(-1)
     ref_label = np.repeat(ancestries.astype(np.int64), lens) if ancestry else None
     plan = plan_from_refs(cols[flat], allele_arr[flat], hap_off, gts.data.shape[1], ref_label)
+    return (plan, never) if unknown_label == "never" else plan
+
+
+def _allele_indices(var_alleles, cols: np.ndarray, allele_strs: list, ancestry: bool) -> np.ndarray:
+    """
+    ``alleles.index(allele)`` (haptools/data/haplotypes.py:1395) -- or ``int(allele != REF)`` for
+    the ancestry classes (haptools/transform.py:130) -- for every haplotype allele at once:
+    REF/ALT1 are resolved with two vectorised string comparisons, only the alleles that match
+    neither (multi-allelic sites) go through ``tuple.index``.
+    """
+    n = len(cols)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    want = np.asarray(allele_strs, dtype=object)
+    ucols, inv = np.unique(cols, return_inverse=True)
+    tuples = [var_alleles[c] for c in ucols]
+    ref = np.asarray([t[0] if len(t) > 0 else None for t in tuples], dtype=object)[inv]
+    is_ref = want == ref
+    if ancestry:
+        return (~is_ref).astype(np.int64)
+    alt = np.asarray([t[1] if len(t) > 1 else None for t in tuples], dtype=object)[inv]
+    out = np.where(is_ref, 0, np.where(want == alt, 1, -1)).astype(np.int64)
+    rest = np.nonzero(out < 0)[0]
+    try:
+        for j in rest:  # ValueError from tuple.index if the allele is not there
+            out[j] = tuples[inv[j]].index(allele_strs[j])
+    except ValueError:
+        raise ValueError("Some alleles were not present in the genotypes")
+    return out
+
+
+def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str = None,
+                         unknown_label: str = "raise"):
+    """
+    Same contract as plan_from_haplotypes_loop (the reference's host steps,
+    haptools/data/haplotypes.py:1375-1401 / haptools/transform.py:103-135, exceptions
+    included) without the per-allele Python loop: the haplotype objects are flattened with list
+    comprehensions, IDs resolve to columns through ``Genotypes.index``'s dict in one pass,
+    allele strings to indices with vectorised comparisons, and plan_from_refs de-duplicates
+    (column, allele[, label]) triples with one np.unique.  (De-duplicating by (column, allele
+    index) instead of the reference's (ID, allele string) yields the same matrix: equal keys
+    give equal planes.)
+    """
+    H = len(haps)
+    lens = np.fromiter((len(h.variants) for h in haps), dtype=np.int64, count=H)
+    hap_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    never = np.zeros(H, dtype=np.bool_)
+    ref_label = None
+    if ancestry:
+        labels = gts.ancestry_labels
+        lab = np.fromiter((labels.get(h.ancestry, -1) for h in haps), dtype=np.int64, count=H)
+        unknown = lab == -1
+        if unknown.any():
+            if unknown_label == "never":
+                never = unknown & (lens > 0)
+                lab = np.where(unknown, 0, lab)
+            else:
+                # uint8 <- -1 raises OverflowError on numpy >= 2, exactly like transform.py:115
+                np.empty(1, dtype=np.uint8)[0] = -1
+        lab.astype(np.uint8, casting="unsafe")  # labels are uint8 in the reference (transform.py:104)
+        ref_label = np.repeat(lab & 0xFF, lens)
+    ids = [v.id for h in haps for v in h.variants]
+    allele_strs = [v.allele for h in haps for v in h.variants]
+    gts.index(samples=False, variants=True)
+    var_idx = gts._var_idx
+    try:
+        cols = np.fromiter(map(var_idx.__getitem__, ids), dtype=np.int64, count=len(ids))
+    except KeyError:
+        missing = [v for v in dict.fromkeys(ids) if v not in var_idx]
+        raise ValueError(
+            f"Variants {set(missing)} are present in {who or 'the haplotypes'} but absent in the provided genotypes"
+        )
+    var_alleles = gts.variants["alleles"] if len(ids) else ()
+    allele_idx = _allele_indices(var_alleles, cols, allele_strs, ancestry)
+    if gts.data.dtype == np.bool_:
+        # the reference builds allele_arr with dtype=bool (haplotypes.py:1398)
+        allele_idx = np.minimum(allele_idx, 1)
+    plan = plan_from_refs(cols, allele_idx, hap_off, gts.data.shape[1], ref_label)
     return (plan, never) if unknown_label == "never" else plan
 
 

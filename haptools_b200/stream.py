@@ -147,3 +147,75 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
             stats.update(read_s=t_read, stream_s=t_packed - t_start, total_device_s=t_done - t_start,
                          total_s=time.perf_counter() - t_start, h2d_bytes=h2d_bytes, chunks=-(-V // chunk) if V else 0)
     return res
+
+
+# ----------------------------------------------------------------------------------------
+# hand-off to the PGEN writer (second half)
+# ----------------------------------------------------------------------------------------
+def hapmajor_from_bits(bits: torch.Tensor, n_samples: int, h0: int, h1: int, dtype=torch.int32,
+                       out: torch.Tensor = None, stream=None) -> torch.Tensor:
+    """
+    Rows h0..h1-1 of the bit-packed result `(tiles, H, 32, 2)` as the haplotype-major
+    `(h1 - h0, 2 n)` matrix `PgenWriter.append_alleles_batch` takes (element 2 s + c), uint8 or
+    int32, on the device (ht_unpack_bits_hapmajor).
+    """
+    if dtype not in (torch.int32, torch.uint8):
+        raise ValueError("dtype must be torch.int32 or torch.uint8")
+    H = int(bits.shape[1])
+    pitch = (2 * n_samples + 3) // 4 * 4
+    if out is None:
+        out = torch.empty((h1 - h0, pitch), dtype=dtype, device=bits.device)
+    check(
+        _cuda.lib().ht_unpack_bits_hapmajor(
+            bits.data_ptr(), n_samples, H, h0, h1 - h0, out.element_size(), out.data_ptr(), int(out.stride(0)),
+            (stream or torch.cuda.current_stream(bits.device)).cuda_stream,
+        ),
+        "ht_unpack_bits_hapmajor",
+    )
+    return out[:, : 2 * n_samples]
+
+
+def pgen_write_batches(bits: torch.Tensor, n_samples: int, chunk_haps: int = 1024, dtype=np.int32):
+    """
+    What `GenotypesPLINK.write` feeds `pgenlib.PgenWriter.append_alleles_batch` chunk by chunk
+    (haptools/data/genotypes.py:1611-1642), produced from the transform's bit-packed result
+    without ever building, transposing or widening the `(n, H, 2)` matrix on the host: yields
+    `(start, end, subset_data, allele_cts)` with `subset_data` a C-contiguous `(end - start, 2 n)`
+    host array of `dtype` (page-locked, reused two yields later -- consume it before asking for
+    the one after next) and `allele_cts` = 2 for every row (a 0/1 matrix never has missing calls
+    and `_num_unique_alleles` floors at 2, genotypes.py:1538-1567).  The expansion of chunk
+    k + 1 and its device->host copy overlap the consumer's work on chunk k.
+    """
+    engine.require_cuda()
+    H = int(bits.shape[1])
+    tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+    dev = bits.device
+    chunk_haps = max(1, min(chunk_haps, H))
+    pitch = (2 * n_samples + 3) // 4 * 4
+    with torch.cuda.device(dev):
+        s_cmp, cur = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        s_cmp.wait_stream(cur)
+        dbuf = [torch.empty((chunk_haps, pitch), dtype=tdt, device=dev) for _ in range(2)]
+        hbuf = [torch.empty((chunk_haps, pitch), dtype=tdt, pin_memory=True) for _ in range(2)]
+        events = [None, None]
+
+        def launch(k):
+            a, b = k * chunk_haps, min(H, (k + 1) * chunk_haps)
+            with torch.cuda.stream(s_cmp):
+                hapmajor_from_bits(bits, n_samples, a, b, tdt, out=dbuf[k % 2], stream=s_cmp)
+                hbuf[k % 2][: b - a].copy_(dbuf[k % 2][: b - a], non_blocking=True)
+                events[k % 2] = s_cmp.record_event()
+
+        n_chunks = -(-H // chunk_haps) if n_samples > 0 else 0
+        if n_chunks:
+            launch(0)
+        for k in range(n_chunks):
+            if k + 1 < n_chunks:
+                launch(k + 1)
+            events[k % 2].synchronize()
+            a, b = k * chunk_haps, min(H, (k + 1) * chunk_haps)
+            host = hbuf[k % 2].numpy()[: b - a, : 2 * n_samples]
+            if pitch != 2 * n_samples:
+                host = np.ascontiguousarray(host)
+            yield a, b, host, np.full(b - a, 2, dtype=np.uint32)
+        cur.wait_stream(s_cmp)

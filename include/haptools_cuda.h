@@ -254,6 +254,20 @@ int ht_count_bits(const uint32_t* bits, int64_t n_samples, int64_t n_haps, uint6
                   void* stream);
 
 /*
+ * Hand-off to the PGEN writer: GenotypesPLINK.write (genotypes.py:1569-1659) transposes the result
+ * to haplotype-major, widens a chunk of rows to int32 and flattens it to (rows, 2 n) for
+ * PgenWriter.append_alleles_batch (:1618-1642).  From the bit-packed result that is a plain
+ * expansion: row r of `out` (r < n_rows) is haplotype h0 + r, element 2 s + c (s < n_samples) its
+ * presence on strand c of sample s, as uint8 (elem_size 1) or int32 (elem_size 4; 16-byte
+ * aligned, pitch a multiple of 4).  out_pitch_elems >= 2 n_samples, in elements.  The
+ * `allele_cts` argument of the writer (_num_unique_alleles, genotypes.py:1538-1567) is 2 for
+ * every row of a 0/1 matrix.
+ */
+int ht_unpack_bits_hapmajor(const uint32_t* bits, int64_t n_samples, int64_t n_haps, int64_t h0,
+                            int64_t n_rows, int elem_size, void* out, int64_t out_pitch_elems,
+                            void* stream);
+
+/*
  * Deterministic synthetic genotypes for the benchmark configs (not part of the
  * reference): fills `gt` (same addressing as ht_pack_u8, all three bytes of a
  * phase-column layout are NOT touched beyond c in {0,1}) from a counter-based hash of

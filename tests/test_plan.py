@@ -191,3 +191,96 @@ def test_quad_tables_restate_the_lists():
     assert qi == len(quads)
     empty = plan_from_refs(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(1, np.int64), p)
     assert empty.quad_tables() == (None, None)
+
+
+# ---------------------------------------------------------------- vectorised planner (N4)
+def _same_plan(a, b):
+    for f in ("n_cols", "var_col", "var_key_off", "key_allele", "key_label", "hap_off", "hap_key"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert (x is None) == (y is None), f
+        if x is not None:
+            np.testing.assert_array_equal(x, y, err_msg=f)
+
+
+@pytest.mark.parametrize("path", _cases.list_golden(), ids=lambda p: p.stem)
+def test_vectorised_planner_equals_reference_loop(path):
+    from haptools_b200.plan import plan_from_haplotypes_loop
+
+    case, haps, gts = _objects(path.name)
+    hap_list = list(haps.data.values())
+    anc = case["kind"] == "ancestry"
+    _same_plan(plan_from_haplotypes(hap_list, gts, ancestry=anc), plan_from_haplotypes_loop(hap_list, gts, ancestry=anc))
+    if anc:
+        (pa, na), (pb, nb) = (f(hap_list, gts, ancestry=True, unknown_label="never") for f in (plan_from_haplotypes, plan_from_haplotypes_loop))
+        _same_plan(pa, pb)
+        np.testing.assert_array_equal(na, nb)
+
+
+def _random_objects(rng, p, H, multi, anc_labels=None, bool_gt=False):
+    gts = (htransform.GenotypesAncestry if anc_labels else data.GenotypesVCF)(None)
+    alleles = [tuple(rng.permutation(["A", "C", "G", "T"])[: (rng.integers(2, 5) if multi else 2)]) for _ in range(p)]
+    gts.variants = np.array([(f"v{i}", "1", i + 1, alleles[i]) for i in range(p)], dtype=gts.variants.dtype)
+    gts.samples = ("s0", "s1")
+    gts.data = np.zeros((2, p, 2), dtype=np.bool_ if bool_gt else np.uint8)
+    if anc_labels:
+        gts.ancestry_labels = anc_labels
+    haps = []
+    for h in range(H):
+        k = int(rng.integers(0, 7))
+        cols = np.sort(rng.choice(p, size=k, replace=False))
+        hp = htransform.HaplotypeAncestry("1", 1, 2, f"H{h}", rng.choice(list(anc_labels))) if anc_labels else data.Haplotype("1", 1, 2, f"H{h}")
+        hp.variants = tuple(data.Variant(int(c) + 1, int(c) + 2, f"v{c}", str(rng.choice(alleles[c]))) for c in cols)
+        haps.append(hp)
+    return haps, gts
+
+
+@pytest.mark.parametrize("multi,anc,bool_gt", [(False, False, False), (True, False, False), (True, False, True), (True, True, False)])
+def test_vectorised_planner_random(multi, anc, bool_gt):
+    from haptools_b200.plan import plan_from_haplotypes_loop
+
+    rng = np.random.default_rng(17)
+    labels = {"YRI": 0, "CEU": 1, "PEL": 2} if anc else None
+    haps, gts = _random_objects(rng, 60, 200, multi, labels, bool_gt)
+    _same_plan(plan_from_haplotypes(haps, gts, ancestry=anc), plan_from_haplotypes_loop(haps, gts, ancestry=anc))
+
+
+def test_vectorised_planner_errors_match_the_loop():
+    from haptools_b200.plan import plan_from_haplotypes_loop
+
+    rng = np.random.default_rng(3)
+    for fn in (plan_from_haplotypes, plan_from_haplotypes_loop):
+        haps, gts = _random_objects(rng, 30, 40, True)
+        bad = data.Haplotype("1", 1, 2, "bad")
+        bad.variants = (data.Variant(1, 2, "v3", "A"), data.Variant(1, 2, "nope", "A"), data.Variant(1, 2, "nada", "C"))
+        with pytest.raises(ValueError, match="absent in the provided genotypes") as e:
+            fn(haps + [bad], gts)
+        assert "nope" in str(e.value) and "nada" in str(e.value)
+        wrong = data.Haplotype("1", 1, 2, "wrong")
+        wrong.variants = (data.Variant(1, 2, "v3", "N"),)
+        with pytest.raises(ValueError, match="Some alleles were not present in the genotypes"):
+            fn(haps + [wrong], gts)
+        gts2 = data.GenotypesVCF(None)
+        gts2.variants = np.array([("d", "1", 1, ("A", "C")), ("d", "1", 2, ("A", "C"))], dtype=gts2.variants.dtype)
+        gts2.data = np.zeros((1, 2, 2), dtype=np.uint8)
+        with pytest.raises(ValueError, match="duplicate variant IDs"):
+            fn(haps, gts2)
+        haps_a, gts_a = _random_objects(rng, 30, 20, False, {"YRI": 0, "CEU": 1})
+        haps_a[4].ancestry = "XXX"
+        with pytest.raises(OverflowError):
+            fn(haps_a, gts_a, ancestry=True)
+        plan, never = fn(haps_a, gts_a, ancestry=True, unknown_label="never")
+        assert never[4] == (len(haps_a[4].variants) > 0) and never.sum() <= 1
+
+
+def test_transform_result_variants_layout():
+    """hap_gts.variants built column-wise equals the reference's tuple-per-haplotype array
+    (haptools/data/haplotypes.py:1369-1372)."""
+    case, haps, gts = _objects("file_example_examplehap.npz")
+    hap_list = list(haps.data.values())
+    want = np.array([(h.id, h.chrom, h.start, ("A", "T")) for h in hap_list], dtype=data.GenotypesVCF(None).variants.dtype)
+    got = np.empty(len(hap_list), dtype=want.dtype)
+    got["id"] = [h.id for h in hap_list]
+    got["chrom"] = [h.chrom for h in hap_list]
+    got["pos"] = [h.start for h in hap_list]
+    got["alleles"].fill(("A", "T"))
+    assert (got == want).all() and all(type(a) is tuple for a in got["alleles"])
