@@ -61,6 +61,7 @@ SIGNATURES = {
     "ht_local_workspace_bytes": (_sz, [_i64, _i64]),
     "ht_transform_u8_local": (_i32, [_p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "ht_unpack_bits_hapmajor": (_i32, [_p, _i64, _i64, _i64, _i64, _i32, _p, _i64, _p]),
+    "ht_format_vcf_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p]),
     "ht_count_bits": (_i32, [_p, _i64, _i64, _p, _p]),
     "ht_synth_gt": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _p]),
     "ht_synth_ancestry": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _i64, _u64, _u32, _u32, _p]),

@@ -109,3 +109,70 @@ extern "C" int ht_unpack_bits_hapmajor(const uint32_t* bits, int64_t n_samples, 
     HT_CUDA_TRY(cudaGetLastError());
     return HT_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// VCF text of the GT columns.  GenotypesVCF.write (haptools/data/genotypes.py:752-813) sets
+// record.samples[s]["GT"] sample by sample in Python and lets htslib print "a|b" per sample,
+// tab-separated, newline-terminated.  For the transform's result (phased, 0/1, never missing)
+// that text is fixed-width: 4 bytes per sample, "a|b\t" ("a|b\n" for the last sample), so a
+// haplotype row is n * 4 bytes and is produced straight from the bit-packed result.
+// warp = one (haplotype, tile); store i covers samples [128 i, 128 i + 128) = 512 contiguous
+// bytes, lane l the 4 samples 128 i + 4 l .. + 3 (one 16-byte store).
+// ---------------------------------------------------------------------------------------
+namespace ht {
+
+__global__ void __launch_bounds__(kHmWarps * 32)
+vcf_gt_text_kernel(const uint32_t* __restrict__ bits, int64_t n_samples, int64_t n_haps, int64_t h0,
+                   int64_t n_rows, int64_t n_tiles, uint8_t* __restrict__ out, int64_t pitch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * kHmWarps + (threadIdx.x >> 5);
+    if (item >= n_rows * n_tiles) return;
+    const int64_t r = item / n_tiles, tile = item % n_tiles;
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(bits) + ((size_t)tile * (size_t)n_haps + (size_t)(h0 + r)) * kTileWords + lane);
+    const int64_t s_tile = tile * kTileSamples;
+    uint8_t* row = out + (size_t)r * (size_t)pitch + 4 * s_tile;
+    const int64_t valid = min((int64_t)kTileSamples, n_samples - s_tile);
+    const int64_t last = n_samples - 1 - s_tile;  // tile-local index of the cohort's last sample
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + (lane >> 3), b = 4 * (lane & 7);
+        const uint32_t x = __shfl_sync(0xffffffffu, w.x, src) >> b, y = __shfl_sync(0xffffffffu, w.y, src) >> b;
+        const int s = 128 * i + 4 * lane;
+        uint32_t t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // '0' + a, '|', '0' + b, '\t'  (little endian)
+            t[e] = 0x09307c30u + ((x >> e) & 1u) + (((y >> e) & 1u) << 16);
+            if (s + e == last) t[e] = (t[e] & 0x00ffffffu) | 0x0a000000u;  // '\n' ends the row
+        }
+        uint8_t* p = row + 4 * s;
+        if (s + 4 <= valid && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(t[0], t[1], t[2], t[3]);
+        } else {
+            for (int e = 0; e < 4; ++e)
+                if (s + e < valid)
+                    for (int k = 0; k < 4; ++k) p[4 * e + k] = (uint8_t)(t[e] >> (8 * k));
+        }
+    }
+}
+
+}  // namespace ht
+
+extern "C" int ht_format_vcf_gt(const uint32_t* bits, int64_t n_samples, int64_t n_haps, int64_t h0,
+                                int64_t n_rows, uint8_t* out, int64_t out_pitch, void* stream) {
+    using namespace ht;
+    if (n_samples < 0 || n_haps < 0 || h0 < 0 || n_rows < 0 || h0 + n_rows > n_haps) return bad_arg("bad haplotype range");
+    if (n_rows == 0 || n_samples == 0) return HT_OK;
+    if (!bits || !out) return bad_arg("bits / out is NULL");
+    if (out_pitch < 4 * n_samples) return bad_arg("out_pitch < 4 * n_samples");
+    const int64_t n_tiles = ht_num_tiles(n_samples);
+    const int64_t blocks = (n_rows * n_tiles + kHmWarps - 1) / kHmWarps;
+    if (blocks > 0x7fffffff) {
+        set_error("too many (haplotype, tile) items (%lld): format fewer rows per call", (long long)(n_rows * n_tiles));
+        return HT_ERR_UNSUPPORTED;
+    }
+    vcf_gt_text_kernel<<<(unsigned)blocks, kHmWarps * 32, 0, (cudaStream_t)stream>>>(bits, n_samples, n_haps, h0, n_rows,
+                                                                                   n_tiles, out, out_pitch);
+    HT_CUDA_TRY(cudaGetLastError());
+    return HT_OK;
+}

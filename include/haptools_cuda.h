@@ -268,6 +268,17 @@ int ht_unpack_bits_hapmajor(const uint32_t* bits, int64_t n_samples, int64_t n_h
                             void* stream);
 
 /*
+ * Hand-off to the VCF writer: GenotypesVCF.write (genotypes.py:752-813) fills
+ * record.samples[s]["GT"] sample by sample in Python and htslib prints "a|b" per sample,
+ * tab-separated, newline-terminated.  For the transform's result (phased, 0/1, never missing)
+ * that text is 4 bytes per sample; row r of `out` receives the n_samples * 4 bytes
+ * "a|b\ta|b\t...a|b\n" of haplotype h0 + r (the nine fixed columns before it are host text).
+ * out_pitch >= 4 * n_samples, in bytes.
+ */
+int ht_format_vcf_gt(const uint32_t* bits, int64_t n_samples, int64_t n_haps, int64_t h0,
+                     int64_t n_rows, uint8_t* out, int64_t out_pitch, void* stream);
+
+/*
  * Deterministic synthetic genotypes for the benchmark configs (not part of the
  * reference): fills `gt` (same addressing as ht_pack_u8, all three bytes of a
  * phase-column layout are NOT touched beyond c in {0,1}) from a counter-based hash of
