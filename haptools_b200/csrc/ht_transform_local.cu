@@ -24,8 +24,6 @@
 //
 // Per tile, in 256-byte records moved through L2: K + A (one kernel) vs
 // sum(block runs) + A + 4 H (two phases).  The planner picks (LocalTables.worthwhile).
-#include <stdlib.h>
-
 #include "ht_transform.cuh"
 
 namespace ht {
@@ -75,13 +73,19 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) {
 }
 
 // ---- phase 1 ---------------------------------------------------------------------------
+// CTA = one block of neighbouring haplotypes x kAndTiles consecutive tiles: the block's key lists
+// are staged once, then per tile one TMA bulk copy brings the block's run of records in, the warps
+// AND their haplotypes out of shared memory, and the next tile's copy is issued.  Three CTAs per
+// SM interleave copy waits with AND phases.
 // bits: record (tl * n_haps + h) for group-local tile tl and haplotype h (caller's order).
+constexpr int kAndTiles = 8;
+
 __global__ void __launch_bounds__(kThreads, 3)
 and_local_bits_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                       const uint32_t* __restrict__ blk_hap_off, const uint32_t* __restrict__ blk_key_lo,
                       const uint32_t* __restrict__ blk_key_cnt, const uint32_t* __restrict__ s_hap_off,
                       const uint32_t* __restrict__ s_hap_key, const uint32_t* __restrict__ hap_order,
-                      int64_t n_haps, uint32_t n_blocks, int64_t tile0, uint32_t dmax,
+                      int64_t n_haps, uint32_t n_blocks, int64_t tile0, int64_t n_tiles, uint32_t dmax,
                       uint32_t* __restrict__ bits, unsigned long long* __restrict__ counts) {
     extern __shared__ __align__(128) uint8_t s_dyn[];
     uint8_t* s_planes = s_dyn;                                                   // dmax * 256 B
@@ -92,24 +96,29 @@ and_local_bits_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, in
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t b = blockIdx.x % n_blocks;
-    const int64_t tl = blockIdx.x / n_blocks, tile = tile0 + tl;
+    const int64_t tl_first = (int64_t)(blockIdx.x / n_blocks) * kAndTiles;
+    const int n_my_tiles = (int)min((int64_t)kAndTiles, n_tiles - tl_first);
     const uint32_t j0 = __ldg(blk_hap_off + b), nh = __ldg(blk_hap_off + b + 1) - j0;
     const uint32_t lo = __ldg(blk_key_lo + b), cnt = __ldg(blk_key_cnt + b);
-    const char* tile_bytes =
-        reinterpret_cast<const char*>(planes) + ((size_t)tile * (size_t)n_keys) * (kRecordWords * 4);
+    const size_t tile_stride = (size_t)n_keys * (kRecordWords * 4);
+    const char* run0 = reinterpret_cast<const char*>(planes) + (size_t)(tile0 + tl_first) * tile_stride;
 
-    // ---- bring the block's run of records in with the TMA (warp 0), stage the lists --------
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_init(&s_bar, 1);
-            if (cnt) mbar_expect_tx(&s_bar, cnt * 256u);
-        }
+    // the run of tile ti -> shared memory: one bulk copy of 16 records per lane of warp 0
+    auto issue_copy = [&](int ti) {
+        if (lane == 0) mbar_expect_tx(&s_bar, cnt * 256u);
         __syncwarp();
+        const char* src = run0 + (size_t)ti * tile_stride + (size_t)lo * 256;
         for (uint32_t r = lane * kLocalChunkRecs; r < cnt; r += 32 * kLocalChunkRecs) {
             const uint32_t nrec = min((uint32_t)kLocalChunkRecs, cnt - r);
-            bulk_g2s(s_planes + (size_t)r * 256, tile_bytes + (size_t)(lo + r) * 256, nrec * 256u, &s_bar);
+            bulk_g2s(s_planes + (size_t)r * 256, src + (size_t)r * 256, nrec * 256u, &s_bar);
         }
+    };
+    if (warp == 0) {
+        if (lane == 0) mbar_init(&s_bar, 1);
+        __syncwarp();
+        if (cnt) issue_copy(0);
     }
+    // ---- stage the block's lists once ------------------------------------------------------
     for (uint32_t i = tid; i <= nh; i += kThreads) s_off[i] = __ldg(s_hap_off + j0 + i);
     for (uint32_t i = tid; i < nh; i += kThreads) s_dst[i] = __ldg(hap_order + j0 + i);
     __syncthreads();
@@ -118,96 +127,121 @@ and_local_bits_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, in
     if (keys_staged)
         for (uint32_t i = tid; i < nk; i += kThreads) s_keys[i] = (uint16_t)__ldg(s_hap_key + kb0 + i);
     __syncthreads();
-    if (cnt) mbar_wait(&s_bar, 0);
 
-    // ---- AND: warp per haplotype, half-warp per record (lane & 15 = 16 bytes of it) ---------
+    // AND: warp per haplotype, half-warp per record (lane & 15 = 16 bytes of it)
     const int half = lane >> 4;
     const uint32_t my16 = 16u * (lane & 15);
-    // validity mask of my two words (samples >= n_samples read as 0, like the planes)
-    const int64_t rem = n_samples - tile * kTileSamples - 64 * (int64_t)(lane & 15);
-    const uint32_t vm0 = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
-    const uint32_t vm1 = rem >= 64 ? 0xffffffffu : (rem <= 32 ? 0u : ((1u << (int)(rem - 32)) - 1u));
-    char* out_bytes = reinterpret_cast<char*>(bits) + ((size_t)tl * (size_t)n_haps) * (kRecordWords * 4) + my16;
+    const uint8_t* my_planes = s_planes + my16;
 
 #pragma unroll 1
-    for (uint32_t hl = warp; hl < nh; hl += kWarps) {
-        const uint32_t kb = s_off[hl] - kb0, ke = s_off[hl + 1] - kb0;
-        uint4 r = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (ke > kb) {
-            const uint32_t last = ke - 1;
-            if (keys_staged) {
-#pragma unroll 4
-                for (uint32_t t = kb + half; t < ke + half; t += 2) {
-                    const uint32_t k = s_keys[min(t, last)];
-                    r = and4(r, *reinterpret_cast<const uint4*>(s_planes + k * 256u + my16));
-                }
-            } else if (cnt) {  // long lists: keys from global memory, records from shared memory
+    for (int ti = 0; ti < n_my_tiles; ++ti) {
+        const int64_t tile = tile0 + tl_first + ti;
+        if (cnt) mbar_wait(&s_bar, ti & 1);
+        // validity mask of my two words (samples >= n_samples read as 0, like the planes)
+        const int64_t rem = n_samples - tile * kTileSamples - 64 * (int64_t)(lane & 15);
+        const uint32_t vm0 = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+        const uint32_t vm1 = rem >= 64 ? 0xffffffffu : (rem <= 32 ? 0u : ((1u << (int)(rem - 32)) - 1u));
+        char* out_bytes = reinterpret_cast<char*>(bits) + ((size_t)(tl_first + ti) * (size_t)n_haps) * (kRecordWords * 4) + my16;
+        const char* tile_bytes = run0 + (size_t)ti * tile_stride;
+
+#pragma unroll 1
+        for (uint32_t hl = warp; hl < nh; hl += kWarps) {
+            const uint32_t kb = s_off[hl] - kb0, len = s_off[hl + 1] - s_off[hl];
+            uint4 r = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if (len) {
+                if (keys_staged && len <= 32u) {
+                    // the list sits in one register per lane; every record address comes over a
+                    // shuffle, so the LDS.128 of a haplotype are independent of each other
+                    const uint32_t mine = (uint32_t)s_keys[kb + min((uint32_t)lane, len - 1)] * 256u;
+#pragma unroll
+                    for (uint32_t t = 0; t < 16; t += 4) {
+                        if (2 * t >= len) break;  // warp-uniform
+                        uint4 v[4];
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; ++u) {
+                            const uint32_t off = __shfl_sync(0xffffffffu, mine, min(2 * (t + u) + half, len - 1));
+                            v[u] = *reinterpret_cast<const uint4*>(my_planes + off);
+                        }
+                        r = and4(r, and4(and4(v[0], v[1]), and4(v[2], v[3])));
+                    }
+                } else if (cnt) {  // long lists (or not staged): keys one by one, records from shared memory
+                    const uint32_t last = kb + len - 1;
 #pragma unroll 2
-                for (uint32_t t = kb + half; t < ke + half; t += 2) {
-                    const uint32_t k = __ldg(s_hap_key + kb0 + min(t, last));
-                    r = and4(r, *reinterpret_cast<const uint4*>(s_planes + k * 256u + my16));
-                }
-            } else {  // block whose run does not fit: global keys, records straight from L2
+                    for (uint32_t t = kb + half; t < kb + len + half; t += 2) {
+                        const uint32_t k = keys_staged ? (uint32_t)s_keys[min(t, last)] : __ldg(s_hap_key + kb0 + min(t, last));
+                        r = and4(r, *reinterpret_cast<const uint4*>(my_planes + k * 256u));
+                    }
+                } else {  // block whose run does not fit: global keys, records straight from L2
+                    const uint32_t last = kb + len - 1;
 #pragma unroll 2
-                for (uint32_t t = kb + half; t < ke + half; t += 2) {
-                    const uint32_t k = __ldg(s_hap_key + kb0 + min(t, last));
-                    r = and4(r, __ldg(reinterpret_cast<const uint4*>(tile_bytes + (size_t)k * 256 + my16)));
+                    for (uint32_t t = kb + half; t < kb + len + half; t += 2) {
+                        const uint32_t k = __ldg(s_hap_key + kb0 + min(t, last));
+                        r = and4(r, __ldg(reinterpret_cast<const uint4*>(tile_bytes + (size_t)k * 256 + my16)));
+                    }
                 }
+                r.x &= __shfl_xor_sync(0xffffffffu, r.x, 16);
+                r.y &= __shfl_xor_sync(0xffffffffu, r.y, 16);
+                r.z &= __shfl_xor_sync(0xffffffffu, r.z, 16);
+                r.w &= __shfl_xor_sync(0xffffffffu, r.w, 16);
             }
-            r.x &= __shfl_xor_sync(0xffffffffu, r.x, 16);
-            r.y &= __shfl_xor_sync(0xffffffffu, r.y, 16);
-            r.z &= __shfl_xor_sync(0xffffffffu, r.z, 16);
-            r.w &= __shfl_xor_sync(0xffffffffu, r.w, 16);
+            r.x &= vm0;
+            r.y &= vm0;
+            r.z &= vm1;
+            r.w &= vm1;
+            const uint32_t h = s_dst[hl];
+            if (counts) {
+                // allele counts for check_maf (haptools/data/genotypes.py:559-625): both half-warps
+                // hold the same words, so count lanes 0-15 only
+                const uint32_t pc = half ? 0u : __popc(r.x) + __popc(r.y) + __popc(r.z) + __popc(r.w);
+                const uint32_t c = __reduce_add_sync(0xffffffffu, pc);
+                if (lane == 0 && c) atomicAdd(counts + h, (unsigned long long)c);
+            }
+            if (!half) *reinterpret_cast<uint4*>(out_bytes + (size_t)h * (kRecordWords * 4)) = r;
         }
-        r.x &= vm0;
-        r.y &= vm0;
-        r.z &= vm1;
-        r.w &= vm1;
-        const uint32_t h = s_dst[hl];
-        if (counts) {
-            // allele counts for check_maf (haptools/data/genotypes.py:559-625): both half-warps
-            // hold the same words, so count lanes 0-15 only
-            const uint32_t pc = half ? 0u : __popc(r.x) + __popc(r.y) + __popc(r.z) + __popc(r.w);
-            const uint32_t c = __reduce_add_sync(0xffffffffu, pc);
-            if (lane == 0 && c) atomicAdd(counts + h, (unsigned long long)c);
+        if (cnt && ti + 1 < n_my_tiles) {
+            __syncthreads();  // everybody is done with this tile's records
+            if (warp == 0) issue_copy(ti + 1);
         }
-        if (!half) *reinterpret_cast<uint4*>(out_bytes + (size_t)h * (kRecordWords * 4)) = r;
     }
 }
 
 // ---- phase 2 ---------------------------------------------------------------------------
-// CTA = 128 haplotypes x kUnpackTiles consecutive tiles; warp = 16 haplotypes; lane = one
-// 32-sample word, both strands.  The 128 records of a (tile, haplotype block) are contiguous
-// (32 KB): one TMA bulk copy per tile, issued one tile ahead so that it lands while the
-// previous tile's bytes are being stored.
-constexpr int kUnpackTiles = 8;
-
+// CTA = (tile, 128 haplotypes); warp = 16 haplotypes; lane = one 32-sample word, both strands.
+// One tile per CTA on purpose: CTAs that loop over several tiles drift apart and the write
+// stream loses its DRAM locality (8 tiles per CTA: 10.0 ms instead of 8.5 ms at n = 200 k, with
+// register prefetch of the next tile's records or with a TMA prefetch alike; an L2 bulk prefetch
+// of the next tile's records from a one-tile CTA changes nothing either: 8.57 vs 8.36 ms).
 template <int kOutVec>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 unpack_bits_u8_kernel(const uint32_t* __restrict__ bits, int64_t n_samples, int64_t n_haps,
                       uint32_t n_hap_blocks, int64_t tile0, int64_t n_tiles, uint8_t* __restrict__ out,
-                      int64_t out_s_samp, int exp_mode) {
-    extern __shared__ __align__(128) uint8_t s_dyn[];  // > 48 KB: dynamic
-    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_dyn);                  // 128 records, 32 KB
-    uint32_t* s_u = s_stage + kHapBlock * kRecordWords;                      // kWarps * kUPitch, 32.9 KB
-    __shared__ __align__(8) uint64_t s_bar;
+                      int64_t out_s_samp) {
+    __shared__ __align__(16) uint32_t s_u[kWarps * kUPitch];  // 32.9 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tl_first = (int64_t)(blockIdx.x / n_hap_blocks) * kUnpackTiles;
-    const int n_my_tiles = (int)min((int64_t)kUnpackTiles, n_tiles - tl_first);
+    const int64_t tl = blockIdx.x / n_hap_blocks, tile = tile0 + tl;
     const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
     const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
     const int hl_begin = warp * kHapsPerWarp;
-    const uint32_t blk_bytes = (uint32_t)n_blk_haps * (kRecordWords * 4);
-    const char* src = reinterpret_cast<const char*>(bits) + ((size_t)tl_first * (size_t)n_haps + (size_t)h0) * (kRecordWords * 4);
-    size_t src_step = (size_t)n_haps * (kRecordWords * 4);
-    if (exp_mode == 1) { src_step = 0; src = reinterpret_cast<const char*>(bits) + (size_t)h0 * (kRecordWords * 4); }
 
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
-        mbar_expect_tx(&s_bar, blk_bytes);
-        bulk_g2s(s_stage, src, blk_bytes, &s_bar);
+    // 16 independent coalesced 256-byte reads per warp; records are read exactly once
+    const uint2* rec = reinterpret_cast<const uint2*>(bits) +
+                       ((size_t)tl * (size_t)n_haps + (size_t)(h0 + hl_begin)) * kTileWords + lane;
+    uint32_t a[32];  // a[2*i + c] = haplotype i of this warp, strand c
+#pragma unroll
+    for (int i = 0; i < kHapsPerWarp; ++i) {
+        uint2 r = make_uint2(0u, 0u);
+        if (hl_begin + i < n_blk_haps)
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(rec + (size_t)i * kTileWords));
+        a[2 * i] = r.x;
+        a[2 * i + 1] = r.y;
     }
-    __syncthreads();  // the barrier is initialised before anybody waits on it
+    transpose32_dev(a);
+
+    // exchange + expand + store: identical to transform_u8_kernel (ht_transform.cu) step 3
+    uint32_t* my_u = s_u + warp * kUPitch + 32 * lane;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) my_u[(j + lane) & 31] = a[j];
+    __syncthreads();
 
     const int half = threadIdx.x & 1;
     const int bw = (threadIdx.x >> 1) & 7;
@@ -216,66 +250,43 @@ unpack_bits_u8_kernel(const uint32_t* __restrict__ bits, int64_t n_samples, int6
     const int n_my_haps = min(8, n_blk_haps - hl0);
     const uint32_t* u_col = s_u + bw * kUPitch;
     const int shift = 16 * half;
+    if (n_my_haps <= 0) return;
+    const int64_t s_base = tile * kTileSamples;
+    const int rows = (int)min((int64_t)kTileSamples, n_samples - s_base);
+    uint8_t* p = out + 2 * (h0 + hl0) + (s_base + c0) * out_s_samp;
     const int64_t p_step = 16 * out_s_samp;
 
-#pragma unroll 1
-    for (int ti = 0; ti < n_my_tiles; ++ti) {
-        const int64_t tile = tile0 + tl_first + ti;
-        if (exp_mode != 2 || ti == 0) mbar_wait(&s_bar, ti & 1);
-        uint32_t a[32];  // a[2*i + c] = haplotype i of this warp, strand c
-        const uint2* rec = reinterpret_cast<const uint2*>(s_stage) + (size_t)hl_begin * kTileWords + lane;
-#pragma unroll
-        for (int i = 0; i < kHapsPerWarp; ++i) {
-            const uint2 r = hl_begin + i < n_blk_haps ? rec[i * kTileWords] : make_uint2(0u, 0u);
-            a[2 * i] = r.x;
-            a[2 * i + 1] = r.y;
-        }
-        transpose32_dev(a);
-        __syncthreads();  // stage consumed by everybody; previous tile's stores have read s_u
-        if (threadIdx.x == 0 && ti + 1 < n_my_tiles && exp_mode != 2) {
-            mbar_expect_tx(&s_bar, blk_bytes);
-            bulk_g2s(s_stage, src + (size_t)(ti + 1) * src_step, blk_bytes, &s_bar);
-        }
-        // exchange + expand + store: identical to transform_u8_kernel (ht_transform.cu) step 3
-        uint32_t* my_u = s_u + warp * kUPitch + 32 * lane;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) my_u[(j + lane) & 31] = a[j];
-        __syncthreads();
-        if (n_my_haps <= 0) continue;
-        const int64_t s_base = tile * kTileSamples;
-        const int rows = (int)min((int64_t)kTileSamples, n_samples - s_base);
-        uint8_t* p = out + 2 * (h0 + hl0) + (s_base + c0) * out_s_samp;
-
-        if (kOutVec == 16 && n_my_haps == 8 && rows == kTileSamples) {
+    if (kOutVec == 16 && n_my_haps == 8 && rows == kTileSamples) {
 #pragma unroll 4
-            for (int L = 0; L < 32; ++L) {
-                const int t = (c0 + L) & 31;
-                const uint32_t w0 = u_col[32 * L + t], w1 = u_col[32 * L + (t ^ 16)];
-                st_stream_v4(p, expand16((w0 >> shift) & 0xffffu));
-                st_stream_v4(p + p_step, expand16((w1 >> shift) & 0xffffu));
-                p += 2 * p_step;
-            }
-            continue;
+        for (int L = 0; L < 32; ++L) {
+            const int t = (c0 + L) & 31;
+            const uint32_t w0 = u_col[32 * L + t], w1 = u_col[32 * L + (t ^ 16)];
+            st_stream_v4(p, expand16((w0 >> shift) & 0xffffu));
+            st_stream_v4(p + p_step, expand16((w1 >> shift) & 0xffffu));
+            p += 2 * p_step;
         }
+        return;
+    }
 #pragma unroll 1
-        for (int it = 0; it < kTileSamples / 16; ++it, p += p_step) {
-            const int sl = it * 16 + c0;
-            if (sl >= rows) break;
-            const int L = it >> 1, j = ((it & 1) << 4) + c0;
-            const uint32_t wbits = (u_col[32 * L + ((j + L) & 31)] >> shift) & 0xffffu;
-            if (kOutVec == 16 && n_my_haps == 8) {
-                st_stream_v4(p, expand16(wbits));
-            } else if (kOutVec >= 2) {
-                for (int q = 0; q < n_my_haps; ++q) {
-                    const uint32_t two = (wbits >> (2 * q)) & 3u;
-                    *reinterpret_cast<uint16_t*>(p + 2 * q) = (uint16_t)((two & 1u) | ((two & 2u) << 7));
-                }
-            } else {
-                for (int q = 0; q < 2 * n_my_haps; ++q) p[q] = (uint8_t)((wbits >> q) & 1u);
+    for (int it = 0; it < kTileSamples / 16; ++it, p += p_step) {
+        const int sl = it * 16 + c0;
+        if (sl >= rows) break;
+        const int L = it >> 1, j = ((it & 1) << 4) + c0;
+        const uint32_t wbits = (u_col[32 * L + ((j + L) & 31)] >> shift) & 0xffffu;
+        if (kOutVec == 16 && n_my_haps == 8) {
+            st_stream_v4(p, expand16(wbits));
+        } else if (kOutVec >= 2) {
+            for (int q = 0; q < n_my_haps; ++q) {
+                const uint32_t two = (wbits >> (2 * q)) & 3u;
+                *reinterpret_cast<uint16_t*>(p + 2 * q) = (uint16_t)((two & 1u) | ((two & 2u) << 7));
             }
+        } else {
+            for (int q = 0; q < 2 * n_my_haps; ++q) p[q] = (uint8_t)((wbits >> q) & 1u);
         }
     }
 }
+
+constexpr int kUnpackTiles = 1;
 
 static int launch_unpack(const uint32_t* bits, int64_t n_samples, int64_t n_haps, int64_t tile0,
                          int64_t n_tiles, uint8_t* out, int64_t out_s_samp, cudaStream_t st) {
@@ -285,25 +296,16 @@ static int launch_unpack(const uint32_t* bits, int64_t n_samples, int64_t n_haps
                     : ((addr | (uintptr_t)out_s_samp) & 1) == 0 ? 2 : 1;
     const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
     const int64_t tiles_per_launch = groups_per_launch * kUnpackTiles;
-    static int exp_mode = getenv("HT_EXP_UNPACK") ? atoi(getenv("HT_EXP_UNPACK")) : 0;
-    constexpr size_t smem = (size_t)(kHapBlock * kRecordWords + kWarps * kUPitch) * sizeof(uint32_t);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        HT_CUDA_TRY(cudaFuncSetAttribute(unpack_bits_u8_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HT_CUDA_TRY(cudaFuncSetAttribute(unpack_bits_u8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HT_CUDA_TRY(cudaFuncSetAttribute(unpack_bits_u8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
         const int64_t nt = min(tiles_per_launch, n_tiles - t0);
         const dim3 grid((unsigned)(((nt + kUnpackTiles - 1) / kUnpackTiles) * n_hb));
         const uint32_t* src = bits + (size_t)t0 * (size_t)n_haps * kRecordWords;
         if (vec == 16)
-            unpack_bits_u8_kernel<16><<<grid, kThreads, smem, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp, exp_mode);
+            unpack_bits_u8_kernel<16><<<grid, kThreads, 0, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp);
         else if (vec == 2)
-            unpack_bits_u8_kernel<2><<<grid, kThreads, smem, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp, exp_mode);
+            unpack_bits_u8_kernel<2><<<grid, kThreads, 0, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp);
         else
-            unpack_bits_u8_kernel<1><<<grid, kThreads, smem, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp, exp_mode);
+            unpack_bits_u8_kernel<1><<<grid, kThreads, 0, st>>>(src, n_samples, n_haps, (uint32_t)n_hb, tile0 + t0, nt, out, out_s_samp);
         HT_CUDA_TRY(cudaGetLastError());
     }
     return HT_OK;
@@ -338,12 +340,14 @@ static int launch_and_local(const uint32_t* planes, int64_t n_samples, int64_t n
         HT_CUDA_TRY(cudaFuncSetAttribute(and_local_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    const int64_t tiles_per_launch = max((int64_t)1, (int64_t)0x7fffffff / t->n_blocks);
+    const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / t->n_blocks);
+    const int64_t tiles_per_launch = groups_per_launch * kAndTiles;
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
         const int64_t nt = min(tiles_per_launch, n_tiles - t0);
-        and_local_bits_kernel<<<dim3((unsigned)(nt * t->n_blocks)), kThreads, smem, st>>>(
+        const unsigned grid = (unsigned)(((nt + kAndTiles - 1) / kAndTiles) * t->n_blocks);
+        and_local_bits_kernel<<<grid, kThreads, smem, st>>>(
             planes, n_samples, n_keys, t->blk_hap_off, t->blk_key_lo, t->blk_key_cnt, t->s_hap_off,
-            t->s_hap_key, t->hap_order, n_haps, (uint32_t)t->n_blocks, tile0 + t0, (uint32_t)t->dmax,
+            t->s_hap_key, t->hap_order, n_haps, (uint32_t)t->n_blocks, tile0 + t0, nt, (uint32_t)t->dmax,
             bits + (size_t)t0 * (size_t)n_haps * kRecordWords, counts);
         HT_CUDA_TRY(cudaGetLastError());
     }
@@ -380,7 +384,7 @@ int ht_unpack_bits_u8(const uint32_t* bits, int64_t n_samples, int64_t n_haps, u
     if (n_samples < 0 || n_haps < 0) return bad_arg("negative size");
     if (n_samples == 0 || n_haps == 0) return HT_OK;
     if (!bits || !out) return bad_arg("bits / out is NULL");
-    if (reinterpret_cast<uintptr_t>(bits) & 15) return bad_arg("bits must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(bits) & 7) return bad_arg("bits must be 8-byte aligned");
     if (out_s_samp < 2 * n_haps) return bad_arg("out_s_samp < 2 * n_haps");
     if ((n_haps + kHapBlock - 1) / kHapBlock > 0x7fffffff) return bad_arg("too many haplotypes");
     return launch_unpack(bits, n_samples, n_haps, 0, ht_num_tiles(n_samples), out, out_s_samp, (cudaStream_t)stream);

@@ -390,7 +390,7 @@ class LocalTables:
         return self.staged_reads + 4 * n_haps < 0.9 * n_refs
 
 
-LOCAL_DMAX = 288  # records staged per block: 72 KB of shared memory, 3 CTAs per SM
+LOCAL_DMAX = 224  # records staged per block: 56 KB of shared memory (+ 8 KB of key lists), 3 CTAs per SM
 LOCAL_MAX_BLOCK = 128  # haplotypes per block at most
 
 

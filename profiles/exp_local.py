@@ -15,10 +15,10 @@ plan = synth.synth_plan(p, H, seed=2)
 out = torch.empty((n, 2 * H), dtype=torch.uint8, device=dev)
 planes = engine.alloc_planes(n, plan.n_keys, dev); planes.random_(0, 2**31 - 1)
 tiles = (n + 1023) // 1024
-for dmax, mb in ((288, 128), (224, 128), (440, 128)):
+for dmax, mb in ((224, 128), (288, 128)):
     dp = engine.DevicePlan(plan, local_dmax=dmax, local_max_block=mb)
     lt, _ = dp.local()
-    if dmax == 288:
+    if dmax == 224:
         ms = timeit(lambda: engine.transform_u8(dp, planes, n, out.data_ptr(), 2 * H, method="direct"))
         print(f"direct: {ms:.2f} ms  out {n*2*H/ms/1e6:.0f} GB/s")
         ref = out.clone() if n <= 200_000 else None

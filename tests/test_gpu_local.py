@@ -110,7 +110,7 @@ def test_local_long_lists_wide_and_empty_haplotypes():
     want = orc.transform_from_csr(gt, plan.key_col().astype(np.int64), plan.key_allele,
                                   plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
     assert want[:, 1].any() and want[:, 7].any() and want[:, 0].all()
-    dplan = engine.DevicePlan(plan)
+    dplan = engine.DevicePlan(plan, local_dmax=288)
     lt, _ = dplan.local()
     assert (lt.blk_key_cnt == 0).any()  # the wide haplotype
     nk = np.diff(lt.s_hap_off.astype(np.int64)[lt.blk_hap_off.astype(np.int64)])
