@@ -17,6 +17,7 @@ Two entry points:
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -107,6 +108,16 @@ class DevicePlan:
         if self.plan.n_haps == 0 or self.plan.n_refs < 4 * self.plan.n_haps:
             return False  # cannot pay for the packed intermediate: skip building the tables
         return self.local()[0].worthwhile(self.plan.n_refs)
+
+
+def device_plan(plan: TransformPlan, device) -> DevicePlan:
+    """The plan's tables on `device`, uploaded once per (plan object, device) and kept with the plan."""
+    device = torch.device(device)
+    cache = plan.__dict__.setdefault("_device_plans", {})
+    key = (device.type, device.index)
+    if key not in cache:
+        cache[key] = DevicePlan(plan, device)
+    return cache[key]
 
 
 def plane_bytes(n_samples: int, n_keys: int) -> int:
@@ -365,13 +376,107 @@ def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
     return t.numpy()[:nbytes].view(dtype).reshape(shape)
 
 
+class _HostPipe:
+    """One device's share of transform_host: double-buffered H2D / compute / D2H on three streams."""
+
+    def __init__(self, dev, plan, dplan, gt, ancestry, bounds, chunk, pack_mode, out, H):
+        self.dev, self.plan, self.pack_mode, self.H = dev, plan, pack_mode, H
+        self.gt, self.ancestry, self.out_ptr = gt, ancestry, out.ctypes.data
+        self.p = gt.shape[1]
+        with torch.cuda.device(dev):
+            self.dplan = dplan if dplan is not None and dplan.device == dev else device_plan(plan, dev)
+            self.nbuf = nbuf = min(2, len(bounds))
+            self.pitch = out_pitch(H)
+            ends = bounds[:1] + bounds[-1:]
+            gt_bytes = max(_region(gt, *b).dev_bytes() for b in ends)
+            self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.anc_buf = [None] * nbuf
+            if plan.has_ancestry:
+                anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in ends)
+                self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.out_buf = [torch.empty(chunk * self.pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.planes = alloc_planes(chunk, plan.n_keys, dev)
+            self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.cur = torch.cuda.current_stream(dev)
+            for st in (self.s_in, self.s_cmp, self.s_out):
+                st.wait_stream(self.cur)
+        self.dense_gt = self.dense_anc = None  # scratch of the on-device re-layout (compute stream only)
+        self.ev_h2d, self.ev_cmp, self.ev_d2h = [None] * nbuf, [None] * nbuf, [None] * nbuf
+        self.keep = []
+        self.k = 0
+
+    def submit(self, s0: int, s1: int) -> None:
+        """Queue chunk [s0, s1) on this device; returns at once (everything is asynchronous)."""
+        plan, dev, H, p = self.plan, self.dev, self.H, self.p
+        b = self.k % self.nbuf
+        self.k += 1
+        rows = s1 - s0
+        s_in, s_cmp, s_out = self.s_in, self.s_cmp, self.s_out
+        with torch.cuda.device(dev):
+            # H2D (the previous user of this input buffer must have been packed)
+            if self.ev_cmp[b] is not None:
+                s_in.wait_event(self.ev_cmp[b])
+            rg = _region(self.gt, s0, s1)
+            self.keep.append(rg.keep)
+            _copy2d(self.gt_buf[b].data_ptr(), rg.dev_pitch(), rg.ptr, rg.pitch, rg.width, rg.rows, _cuda.HT_COPY_H2D, s_in)
+            ra = None
+            if plan.has_ancestry:
+                ra = _region(self.ancestry, s0, s1)
+                self.keep.append(ra.keep)
+                _copy2d(self.anc_buf[b].data_ptr(), ra.dev_pitch(), ra.ptr, ra.pitch, ra.width, ra.rows, _cuda.HT_COPY_H2D, s_in)
+            self.ev_h2d[b] = s_in.record_event()
+            # compute (the previous result in this output buffer must have left)
+            s_cmp.wait_event(self.ev_h2d[b])
+            if self.ev_d2h[b] is not None:
+                s_cmp.wait_event(self.ev_d2h[b])
+            g_ptr, g_str = self.gt_buf[b].data_ptr(), rg.dev_strides()
+            a_ptr, a_str = (_ptr(self.anc_buf[b]), ra.dev_strides()) if ra else (0, (0, 0, 0))
+            if self.pack_mode == _cuda.HT_PACK_AUTO:
+                # arrays that interleave the phase column (or other odd strides): dense re-layout
+                # on the device so that the fast pack kernels apply (PCIe is the bound here)
+                if not _fast_layout(g_str):
+                    d_str, d_bytes = rg.dense(rows, p)
+                    if self.dense_gt is None or self.dense_gt.numel() < d_bytes:
+                        with torch.cuda.stream(s_cmp):
+                            self.dense_gt = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
+                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, p, self.dense_gt.data_ptr(),
+                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    g_ptr, g_str = self.dense_gt.data_ptr(), d_str
+                if ra and not _fast_layout(a_str):
+                    d_str, d_bytes = ra.dense(rows, p)
+                    if self.dense_anc is None or self.dense_anc.numel() < d_bytes:
+                        with torch.cuda.stream(s_cmp):
+                            self.dense_anc = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
+                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, p, self.dense_anc.data_ptr(),
+                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    a_ptr, a_str = self.dense_anc.data_ptr(), d_str
+            pack(self.dplan, g_ptr, g_str, rows, self.planes, a_ptr, a_str, None, self.pack_mode, s_cmp)
+            transform_u8(self.dplan, self.planes, rows, self.out_buf[b].data_ptr(), self.pitch, s_cmp)
+            self.ev_cmp[b] = s_cmp.record_event()
+            # D2H
+            s_out.wait_event(self.ev_cmp[b])
+            _copy2d(self.out_ptr + s0 * 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, s_out)
+            self.ev_d2h[b] = s_out.record_event()
+
+    def finish(self) -> None:
+        with torch.cuda.device(self.dev):
+            self.s_out.synchronize()
+            self.s_cmp.synchronize()
+            self.s_in.synchronize()
+            self.cur.wait_stream(self.s_out)
+
+
 def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,
                    chunk_samples: int = None, out: np.ndarray = None, pin_output: bool = None,
-                   dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO) -> np.ndarray:
+                   dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO, devices=None) -> np.ndarray:
     """
     gt (n, p, 2|3) uint8/bool host array (a view is fine: VCF-style transposed, PGEN-style
     with a phase column, C-contiguous ...) -> (n, H, 2) numpy bool, bit-identical to the
     reference's ``hap_gts.data``.
+
+    devices  optional list of CUDA devices (or "all"): sample chunks are dealt round-robin to
+             them -- samples shard with no communication, and every GPU brings its own PCIe
+             link, which is what bounds this call.  Default: the one current (or `device`) GPU.
     """
     require_cuda()
     if gt.ndim != 3 or gt.shape[2] < 2 or gt.dtype not in (np.uint8, np.bool_):
@@ -383,7 +488,18 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
         if ancestry is None or ancestry.shape[:2] != gt.shape[:2] or ancestry.shape[2] < 2 or ancestry.dtype != np.uint8:
             raise ValueError("ancestry must be a uint8 array shaped like the genotypes")
     H = plan.n_haps
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if devices is None and device is None and os.environ.get("HAPTOOLS_B200_DEVICES"):
+        # e.g. HAPTOOLS_B200_DEVICES=all or =0,1,2,3: lets Haplotypes.transform (which has no device
+        # argument, like the reference's) use every GPU of the box
+        env = os.environ["HAPTOOLS_B200_DEVICES"].strip()
+        devices = "all" if env.lower() == "all" else [int(x) for x in env.split(",") if x.strip()]
+    if devices == "all":
+        devs = [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+    elif devices:
+        devs = [torch.device(d) if not isinstance(d, int) else torch.device("cuda", d) for d in devices]
+    else:
+        devs = [torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)]
+    devs = [torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device()) for d in devs]
     if out is None:
         nbytes = n * H * 2
         if pin_output is None:
@@ -394,81 +510,16 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
     result = out.view(np.bool_)
     if n == 0 or H == 0:
         return result
-    with torch.cuda.device(dev):
-        if dplan is None:
-            dplan = DevicePlan(plan, dev)
-        chunk = chunk_samples or default_chunk(n, p, H)
-        chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
-        bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
-        nbuf = min(2, len(bounds))
-        pitch = out_pitch(H)
-        regs = [_region(gt, *bounds[0])]
-        gt_bytes = max(_region(gt, *b).dev_bytes() for b in bounds[:1] + bounds[-1:])
-        gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-        anc_buf = [None] * nbuf
-        if plan.has_ancestry:
-            anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in bounds[:1] + bounds[-1:])
-            anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-        out_buf = [torch.empty(chunk * pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-        planes = alloc_planes(chunk, plan.n_keys, dev)
-        s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        cur = torch.cuda.current_stream(dev)
-        for s in (s_in, s_cmp, s_out):
-            s.wait_stream(cur)
-        dense_gt = dense_anc = None  # scratch of the on-device re-layout (compute stream only)
-        ev_h2d = [None] * nbuf
-        ev_cmp = [None] * nbuf
-        ev_d2h = [None] * nbuf
-        keep = []
-        del regs
-        out_ptr = out.ctypes.data
-        for k, (s0, s1) in enumerate(bounds):
-            b = k % nbuf
-            rows = s1 - s0
-            # H2D (the previous user of this input buffer must have been packed)
-            if ev_cmp[b] is not None:
-                s_in.wait_event(ev_cmp[b])
-            rg = _region(gt, s0, s1)
-            keep.append(rg.keep)
-            _copy2d(gt_buf[b].data_ptr(), rg.dev_pitch(), rg.ptr, rg.pitch, rg.width, rg.rows, _cuda.HT_COPY_H2D, s_in)
-            ra = None
-            if plan.has_ancestry:
-                ra = _region(ancestry, s0, s1)
-                keep.append(ra.keep)
-                _copy2d(anc_buf[b].data_ptr(), ra.dev_pitch(), ra.ptr, ra.pitch, ra.width, ra.rows, _cuda.HT_COPY_H2D, s_in)
-            ev_h2d[b] = s_in.record_event()
-            # compute (the previous result in this output buffer must have left)
-            s_cmp.wait_event(ev_h2d[b])
-            if ev_d2h[b] is not None:
-                s_cmp.wait_event(ev_d2h[b])
-            g_ptr, g_str = gt_buf[b].data_ptr(), rg.dev_strides()
-            a_ptr, a_str = (_ptr(anc_buf[b]), ra.dev_strides()) if ra else (0, (0, 0, 0))
-            if pack_mode == _cuda.HT_PACK_AUTO:
-                # arrays that interleave the phase column (or other odd strides): dense re-layout
-                # on the device so that the fast pack kernels apply (PCIe is the bound here)
-                if not _fast_layout(g_str):
-                    d_str, d_bytes = rg.dense(rows, p)
-                    if dense_gt is None or dense_gt.numel() < d_bytes:
-                        dense_gt = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, p, dense_gt.data_ptr(),
-                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
-                    g_ptr, g_str = dense_gt.data_ptr(), d_str
-                if ra and not _fast_layout(a_str):
-                    d_str, d_bytes = ra.dense(rows, p)
-                    if dense_anc is None or dense_anc.numel() < d_bytes:
-                        dense_anc = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, p, dense_anc.data_ptr(),
-                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
-                    a_ptr, a_str = dense_anc.data_ptr(), d_str
-            pack(dplan, g_ptr, g_str, rows, planes, a_ptr, a_str, None, pack_mode, s_cmp)
-            transform_u8(dplan, planes, rows, out_buf[b].data_ptr(), pitch, s_cmp)
-            ev_cmp[b] = s_cmp.record_event()
-            # D2H
-            s_out.wait_event(ev_cmp[b])
-            _copy2d(out_ptr + s0 * 2 * H, 2 * H, out_buf[b].data_ptr(), pitch, 2 * H, rows, _cuda.HT_COPY_D2H, s_out)
-            ev_d2h[b] = s_out.record_event()
-        s_out.synchronize()
-        s_cmp.synchronize()
-        s_in.synchronize()
-        cur.wait_stream(s_out)
+    chunk = chunk_samples or default_chunk(n, p, H)
+    if len(devs) > 1 and not chunk_samples:  # at least two chunks per device keep its three streams busy
+        chunk = min(chunk, max(TILE, -(-n // (2 * len(devs))) // TILE * TILE))
+    chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
+    bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+    devs = devs[: len(bounds)]
+    pipes = [_HostPipe(d, plan, dplan, gt, ancestry, bounds[i :: len(devs)], chunk, pack_mode, out, H)
+             for i, d in enumerate(devs)]
+    for k, (s0, s1) in enumerate(bounds):
+        pipes[k % len(pipes)].submit(s0, s1)
+    for pipe in pipes:
+        pipe.finish()
     return result

@@ -560,3 +560,26 @@ def test_config_ukb_scale_shard_slice_and_checksums():
         want = orc.transform_from_csr(sub, plan.key_col().astype(np.int64), plan.key_allele,
                                       plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
         np.testing.assert_array_equal(out[s0 : s0 + 64].cpu().numpy().view(np.bool_), want)
+
+
+def test_host_pipeline_round_robin_over_devices():
+    """transform_host(devices=...): sample chunks dealt round-robin to the GPUs of the box (on a
+    one-GPU box the same code path runs with a single device)."""
+    rng = np.random.default_rng(12)
+    n, p, H = 9000, 64, 90
+    gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=3, missing=0.02)
+    for devices in ([0], "all"):
+        got = engine.transform_host(gt, plan, ancestry=anc, chunk_samples=1024, devices=devices)
+        np.testing.assert_array_equal(got, want)
+    if torch.cuda.device_count() >= 2:
+        got = engine.transform_host(gt, plan, ancestry=anc, devices=[1, 0])  # chunk size derived from the device count
+        np.testing.assert_array_equal(got, want)
+        with torch.cuda.device(1):
+            got = engine.transform_host(gt[:, :, :2], plan_from_refs(*_plain_refs(plan), p), devices="all")
+        assert got.shape == (n, H, 2)
+
+
+def _plain_refs(plan):
+    """(ref_col, ref_allele, hap_off) of a plan with its ancestry labels dropped."""
+    key_col = plan.key_col().astype(np.int64)
+    return key_col[plan.hap_key.astype(np.int64)], plan.key_allele[plan.hap_key.astype(np.int64)].astype(np.int64), plan.hap_off.astype(np.int64)
