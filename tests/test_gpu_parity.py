@@ -583,3 +583,48 @@ def _plain_refs(plan):
     """(ref_col, ref_allele, hap_off) of a plan with its ancestry labels dropped."""
     key_col = plan.key_col().astype(np.int64)
     return key_col[plan.hap_key.astype(np.int64)], plan.key_allele[plan.hap_key.astype(np.int64)].astype(np.int64), plan.hap_off.astype(np.int64)
+
+
+def test_size_independent_properties_at_scale():
+    """Properties that need no oracle, at a size the oracle cannot reach (120k samples x 20k
+    variants x 30k haplotypes = 7.2e9 hap-calls):
+      * union: a haplotype made of the alleles of two others is present exactly where both are;
+      * sample independence: a permuted cohort gives the permuted result;
+      * counts fused into the kernel == popcount of the packed result == column sums."""
+    n, p, H = 120_000, 20_000, 30_000
+    dev = torch.device("cuda")
+    ref_col, ref_allele, hap_off, _ = synth.synth_haplotype_refs(p, H, 7, max_alleles=8)
+    # the last H/3 haplotypes are unions of two earlier ones
+    third = H // 3
+    rng = np.random.default_rng(1)
+    pairs = rng.integers(0, 2 * third, size=(third, 2))
+    cols, alls, offs = [ref_col[: hap_off[2 * third]]], [ref_allele[: hap_off[2 * third]]], list(hap_off[: 2 * third + 1])
+    for a, b in pairs:
+        idx = np.concatenate([np.arange(hap_off[a], hap_off[a + 1]), np.arange(hap_off[b], hap_off[b + 1])])
+        cols.append(ref_col[idx]); alls.append(ref_allele[idx]); offs.append(offs[-1] + len(idx))
+    plan = plan_from_refs(np.concatenate(cols), np.concatenate(alls), np.asarray(offs), p)
+    H = plan.n_haps
+    dplan = engine.DevicePlan(plan, dev)
+    gt = torch.empty((n, p, 2), dtype=torch.uint8, device=dev)
+    _cuda.check(_cuda.lib().ht_synth_gt(gt.data_ptr(), *gt.stride(), n, p, 0, 5, 1, 30, 0), "synth")
+    counts = torch.empty(H, dtype=torch.int64, device=dev)
+    out = engine.transform_device(gt, dplan, counts=counts)
+    torch.cuda.synchronize()
+    assert int(counts.sum()) > 0
+    # union property, checked on the device column block by column block
+    pa, pb = torch.from_numpy(pairs[:, 0]).to(dev), torch.from_numpy(pairs[:, 1]).to(dev)
+    for lo in range(0, third, 2000):
+        hi = min(third, lo + 2000)
+        both = out[:, pa[lo:hi]] & out[:, pb[lo:hi]]
+        assert torch.equal(out[:, 2 * third + lo : 2 * third + hi], both)
+    # counts: fused == column sums == popcount of the packed form
+    sums = torch.zeros(H, dtype=torch.int64, device=dev)
+    for lo in range(0, n, 20_000):
+        sums += out[lo : lo + 20_000].sum(dim=(0, 2), dtype=torch.int64)
+    assert torch.equal(counts, sums)
+    bits = engine.transform_device(gt, dplan, fmt="bits")
+    assert torch.equal(engine.count_bits(bits, n, H), sums)
+    # sample independence on a permuted slice of the cohort
+    perm = torch.randperm(4096, device=dev)
+    sub = engine.transform_device(gt[:4096][perm].contiguous(), dplan)
+    assert torch.equal(sub, out[:4096][perm])
