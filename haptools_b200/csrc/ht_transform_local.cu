@@ -335,11 +335,8 @@ static int launch_and_local(const uint32_t* planes, int64_t n_samples, int64_t n
                             const ht_local_tables* t, int64_t n_haps, int64_t tile0, int64_t n_tiles,
                             uint32_t* bits, unsigned long long* counts, cudaStream_t st) {
     const size_t smem = local_smem_bytes(t->dmax);
-    static thread_local size_t smem_set = 0;  // per host thread: the attribute call is cheap but not free
-    if (smem > smem_set) {
-        HT_CUDA_TRY(cudaFuncSetAttribute(and_local_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    // per launch: the attribute is per device, and a caller may drive several devices from one thread
+    HT_CUDA_TRY(cudaFuncSetAttribute(and_local_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / t->n_blocks);
     const int64_t tiles_per_launch = groups_per_launch * kAndTiles;
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
