@@ -145,14 +145,11 @@ def transform_to_vcf(hp, gts, fileobj, maf: float = None, ancestry: bool = False
     bits = None
     if len(haps) and n:
         with torch.cuda.device(dev):
-            dplan = engine.DevicePlan(plan, dev)
-            # (genotypes of a cohort that does not fit the device go through engine.transform_host /
-            # stream.transform_pgen_stream, which produce the same packed result chunk by chunk)
-            gt = torch.from_numpy(np.ascontiguousarray(gts.data[:, :, :2]).view(np.uint8)).to(dev)
-            anc = torch.from_numpy(np.ascontiguousarray(gts.ancestry[:, :, :2])).to(dev) if ancestry else None
-            bits = engine.transform_device(gt, dplan, ancestry=anc, fmt="bits")
+            # sample chunks stream through the device; only the bit-packed result stays resident
+            bits, counts = engine.transform_host_bits(gts.data, plan, ancestry=gts.ancestry if ancestry else None,
+                                                      device=dev, counts=True)
             if maf is not None:
-                keep = maf_keep(engine.count_bits(bits, n, len(haps)), n, maf)
+                keep = maf_keep(counts, n, maf)
     elif maf is not None and len(haps):
         keep = np.arange(len(haps))
     return write_vcf_from_bits(fileobj, variants, gts.samples, bits, n, keep=keep)

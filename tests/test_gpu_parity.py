@@ -628,3 +628,21 @@ def test_size_independent_properties_at_scale():
     perm = torch.randperm(4096, device=dev)
     sub = engine.transform_device(gt[:4096][perm].contiguous(), dplan)
     assert torch.equal(sub, out[:4096][perm])
+
+
+@pytest.mark.parametrize("lay", ["C", "F", "C3", "F3"])
+def test_host_to_resident_bits(lay):
+    """engine.transform_host_bits: chunked upload, packed result resident on the device, counts."""
+    from haptools_b200 import dist as hdist
+
+    rng = np.random.default_rng(31)
+    n, p, H = 4500, 56, 61
+    gt, anc, plan, want = _random_arrays(rng, n, p, H, n_pops=3 if lay in ("C", "F") else 0, multi=lay not in ("C", "F"), missing=0.02)
+    arr = _layouts(gt)[lay]
+    a = _layouts(anc)[lay] if anc is not None else None
+    for chunk in (None, 1024, 2048):
+        bits, counts = engine.transform_host_bits(arr, plan, ancestry=a, chunk_samples=chunk, counts=True)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(hdist.unpack_result_bits(bits.cpu().numpy().view(np.uint32), n), want)
+        np.testing.assert_array_equal(counts.cpu().numpy(), want.sum(axis=(0, 2)))
+    assert engine.transform_host_bits(arr, plan, ancestry=a).shape == ((n + 1023) // 1024, H, 32, 2)
