@@ -178,32 +178,74 @@ __device__ __forceinline__ uint4 load_chunk16(const uint8_t* p, int nvalid) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// one (tile, variant) item of the variant-major kernel; executed by a whole warp
+// one (tile, variant) item of the variant-major kernel; executed by a whole warp.  The row loads of
+// an item (vm_fetch) are issued one item AHEAD of its arithmetic (pack_vm_item), so a warp always
+// has 2 KB (4 KB with ancestry) in flight instead of waiting out every item's DRAM latency.
 template <bool kAnc>
-__device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, int64_t v, int lane) {
+struct VmItem {
+    uint4 x[4];             // genotype bytes: 4 chunks of 8 samples x 2 strands
+    uint4 q[kAnc ? 4 : 1];  // ancestry bytes, same chunks
+    uint32_t kb, ke;        // the variant's keys
+};
+
+template <bool kAnc>
+__device__ __forceinline__ void vm_fetch(const PackArgs& a, int64_t tile, int64_t v, int lane, VmItem<kAnc>& it) {
     const uint32_t col = __ldg(a.var_col + v);
-    const uint32_t kb = __ldg(a.var_key_off + v), ke = __ldg(a.var_key_off + v + 1);
+    it.kb = __ldg(a.var_key_off + v);
+    it.ke = __ldg(a.var_key_off + v + 1);
     const int rows = (int)min((int64_t)kTileSamples, a.n - tile * kTileSamples);
     const uint8_t* g = a.gt + (int64_t)col * a.gv + tile * (2 * kTileSamples);
     const uint8_t* l = kAnc ? a.anc + (int64_t)col * a.av + tile * (2 * kTileSamples) : nullptr;
+    if (rows == kTileSamples) {  // every tile but the last: four unconditional 16-byte loads per lane
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            it.x[j] = __ldg(reinterpret_cast<const uint4*>(g) + j * 32 + lane);
+            if (kAnc) it.q[j] = __ldg(reinterpret_cast<const uint4*>(l) + j * 32 + lane);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = j * 32 + lane;
+        const int nvalid = rows - 8 * c;
+        it.x[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (nvalid > 0) it.x[j] = load_chunk16(g + 16 * c, nvalid);
+        if (kAnc) {
+            it.q[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (nvalid > 0) it.q[j] = load_chunk16(l + 16 * c, nvalid);
+        }
+    }
+}
+
+// Lane l holds, for j = 0..3, the byte M.byte[j] = 8 sample bits of chunk 32 j + l, i.e. byte (l & 3)
+// of word 8 j + (l >> 2) of one strand's plane.  Returns word `lane` of the plane: a 4x4 byte transpose
+// inside every group of 4 lanes (2 shuffles) leaves lane 4 g + j with the whole word 8 j + g, one more
+// shuffle brings word L to lane L -- so that a warp stores a record with ONE coalesced instruction.
+__device__ __forceinline__ uint32_t vm_gather_word(uint32_t M, int lane) {
+    const uint32_t p = __shfl_xor_sync(0xffffffffu, M, 1);
+    const uint32_t y = prmt(M, p, (lane & 1) ? 0x3715u : 0x6240u);  // even: [M0 p0 M2 p2]; odd: [p1 M1 p3 M3]
+    const uint32_t q = __shfl_xor_sync(0xffffffffu, y, 2);
+    const uint32_t w = prmt(y, q, (lane & 2) ? 0x3276u : 0x5410u);  // lane 4g+j: bytes j of lanes 4g..4g+3
+    return __shfl_sync(0xffffffffu, w, 4 * (lane & 7) + (lane >> 3));
+}
+
+template <bool kAnc>
+__device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, const VmItem<kAnc>& it, int lane) {
+    const uint32_t kb = it.kb, ke = it.ke;
 
     // y = strand-0 bytes, z = strand-1 bytes of the lane's 4 chunks (8 samples each)
     uint32_t y[4][2], z[4][2], ay[4][2], az[4][2];
     uint32_t fl = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int c = j * 32 + lane;
-        const int nvalid = rows - 8 * c;
-        uint4 x = make_uint4(0u, 0u, 0u, 0u);
-        if (nvalid > 0) x = load_chunk16(g + 16 * c, nvalid);
+        const uint4 x = it.x[j];
         if (a.flags) fl |= qc_flags4(x.x) | qc_flags4(x.y) | qc_flags4(x.z) | qc_flags4(x.w);
         y[j][0] = prmt(x.x, x.y, 0x6420);
         y[j][1] = prmt(x.z, x.w, 0x6420);
         z[j][0] = prmt(x.x, x.y, 0x7531);
         z[j][1] = prmt(x.z, x.w, 0x7531);
         if (kAnc) {
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (nvalid > 0) q = load_chunk16(l + 16 * c, nvalid);
+            const uint4 q = it.q[j];
             ay[j][0] = prmt(q.x, q.y, 0x6420);
             ay[j][1] = prmt(q.z, q.w, 0x6420);
             az[j][0] = prmt(q.x, q.y, 0x7531);
@@ -211,6 +253,7 @@ __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, in
         }
     }
     publish_flags(a.flags, fl);
+    const uint32_t vm = valid_mask(a.n, tile, lane);  // lane l stores word l of a record
 
     if (!kAnc) {
         // Biallelic single pass: if the variant's keys are just alleles {0, 1} and no byte of the
@@ -229,32 +272,26 @@ __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, in
             // keys are sorted by allele: (0), (1) or (0, 1)
             const int k_ref = al0 == 0u ? (int)kb : -1;
             const int k_alt = al0 == 1u ? (int)kb : (nk == 2 ? (int)kb + 1 : -1);
+            uint32_t M0 = 0u, M1 = 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t u0 = (y[j][0] & 0x01010101u) + ((y[j][1] & 0x01010101u) << 4);
                 const uint32_t u1 = (z[j][0] & 0x01010101u) + ((z[j][1] & 0x01010101u) << 4);
-                const uint32_t m0 = ((u0 * 0x00204081u) >> 21) & 0xffu;  // 8 samples, strand 0
-                const uint32_t m1 = ((u1 * 0x00204081u) >> 21) & 0xffu;  // 8 samples, strand 1
-                uint32_t t = (m0 | (m1 << 16)) << (8 * (lane & 1));
-                t |= __shfl_xor_sync(0xffffffffu, t, 1);
-                const uint32_t u = __shfl_xor_sync(0xffffffffu, t, 2);
-                const uint32_t lo = (lane & 2) ? u : t, hi = (lane & 2) ? t : u;
-                if ((lane & 3) == 0) {
-                    const int word = 8 * j + (lane >> 2);
-                    const uint32_t vm = valid_mask(a.n, tile, word);
-                    const uint32_t w0 = prmt(lo, hi, 0x5410), w1 = prmt(lo, hi, 0x7632);
-                    if (k_alt >= 0) record(a, tile, (uint32_t)k_alt)[word] = make_uint2(w0 & vm, w1 & vm);
-                    if (k_ref >= 0) record(a, tile, (uint32_t)k_ref)[word] = make_uint2(~w0 & vm, ~w1 & vm);
-                }
+                M0 |= (((u0 * 0x00204081u) >> 21) & 0xffu) << (8 * j);  // 8 samples, strand 0
+                M1 |= (((u1 * 0x00204081u) >> 21) & 0xffu) << (8 * j);  // 8 samples, strand 1
             }
+            const uint32_t w0 = vm_gather_word(M0, lane), w1 = vm_gather_word(M1, lane);
+            if (k_alt >= 0) record(a, tile, (uint32_t)k_alt)[lane] = make_uint2(w0 & vm, w1 & vm);
+            if (k_ref >= 0) record(a, tile, (uint32_t)k_ref)[lane] = make_uint2(~w0 & vm, ~w1 & vm);
             return;
         }
     }
 
+#pragma unroll 1
     for (uint32_t k = kb; k < ke; ++k) {
         const uint32_t pat = (uint32_t)__ldg(a.key_allele + k) * 0x01010101u;
         const uint32_t lpat = kAnc ? (uint32_t)__ldg(a.key_label + k) * 0x01010101u : 0u;
-        uint2* rec = record(a, tile, k);
+        uint32_t M0 = 0u, M1 = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t f0a = eq_bytes_msb(y[j][0], pat), f0b = eq_bytes_msb(y[j][1], pat);
@@ -265,32 +302,37 @@ __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, in
                 f1a &= eq_bytes_msb(az[j][0], lpat);
                 f1b &= eq_bytes_msb(az[j][1], lpat);
             }
-            const uint32_t m0 = nib(f0a) | (nib(f0b) << 4);  // 8 samples, strand 0
-            const uint32_t m1 = nib(f1a) | (nib(f1b) << 4);  // 8 samples, strand 1
-            // lanes 4m..4m+3 hold the 4 bytes of word 8*j + m: merge them
-            uint32_t t = (m0 | (m1 << 16)) << (8 * (lane & 1));
-            t |= __shfl_xor_sync(0xffffffffu, t, 1);
-            const uint32_t u = __shfl_xor_sync(0xffffffffu, t, 2);
-            const uint32_t lo = (lane & 2) ? u : t, hi = (lane & 2) ? t : u;
-            if ((lane & 3) == 0) {
-                const int word = 8 * j + (lane >> 2);
-                const uint32_t vm = valid_mask(a.n, tile, word);
-                rec[word] = make_uint2(prmt(lo, hi, 0x5410) & vm, prmt(lo, hi, 0x7632) & vm);
-            }
+            M0 |= (nib(f0a) | (nib(f0b) << 4)) << (8 * j);  // 8 samples, strand 0
+            M1 |= (nib(f1a) | (nib(f1b) << 4)) << (8 * j);  // 8 samples, strand 1
         }
+        record(a, tile, k)[lane] = make_uint2(vm_gather_word(M0, lane) & vm, vm_gather_word(M1, lane) & vm);
     }
 }
-
-// Grid-stride over (tile, variant) items, tile-major: a warp does only 2 KB of work per item,
-// so short-lived CTAs (one item per warp) are bound by CTA launch rate, not by memory.
 template <bool kAnc>
-__global__ void __launch_bounds__(kPackThreads)
+__global__ void __launch_bounds__(kPackThreads, kAnc ? 2 : 4)
 pack_vm_kernel(const PackArgs a, int64_t n_tiles) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_items = n_tiles * a.n_vars;
-    for (int64_t item = (int64_t)blockIdx.x * kPackWarps + warp; item < n_items;
-         item += (int64_t)gridDim.x * kPackWarps)
-        pack_vm_item<kAnc>(a, item / a.n_vars, item % a.n_vars, lane);
+    const int64_t n_items = n_tiles * a.n_vars, stride = (int64_t)gridDim.x * kPackWarps;
+    int64_t item = (int64_t)blockIdx.x * kPackWarps + warp;
+    if (item >= n_items) return;
+    // (tile, variant) of an item advance by a constant step: no 64-bit division in the loop
+    const int64_t step_t = stride / a.n_vars, step_v = stride % a.n_vars;
+    int64_t tile = item / a.n_vars, v = item % a.n_vars;
+    VmItem<kAnc> cur, nxt;
+    vm_fetch<kAnc>(a, tile, v, lane, cur);
+#pragma unroll 1
+    for (; item < n_items; item += stride) {
+        int64_t tile_n = tile + step_t, v_n = v + step_v;
+        if (v_n >= a.n_vars) {
+            v_n -= a.n_vars;
+            ++tile_n;
+        }
+        if (item + stride < n_items) vm_fetch<kAnc>(a, tile_n, v_n, lane, nxt);
+        pack_vm_item<kAnc>(a, tile, cur, lane);
+        cur = nxt;
+        tile = tile_n;
+        v = v_n;
+    }
 }
 
 // -----------------------------------------------------------------------------------------
