@@ -26,8 +26,10 @@
 namespace ht {
 
 __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
-    // planes are re-read by every haplotype that uses the key: keep them in L1/L2
-#if defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 1  // experiments (profiles/)
+    // Plane records are re-read by every haplotype that uses the key (about 11 times per tile on the
+    // UKB-scale plan) while 8x as many result bytes stream through L2: ask L2 to evict them last
+    // (createpolicy is pure -- not volatile -- so the compiler keeps one copy per kernel).
+#if defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 1  // experiments (profiles/exp_variants.py)
     uint2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
@@ -39,8 +41,14 @@ __device__ __forceinline__ uint2 ld_plane(const uint2* p) {
     uint2 v;
     asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
-#else
+#elif defined(HT_EXP_LD_MODE) && HT_EXP_LD_MODE == 5  // plain read-only load, no L2 hint (the v5 default)
     return __ldg(p);
+#else
+    uint2 v;
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
 #endif
 }
 
