@@ -441,8 +441,8 @@ def run_b200(args):
     pack_gbs = ab["pack"] / (pack_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "transform_u8_kernel" if not two_phase else "and_local_bits_kernel + unpack_bits_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
-        "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.079), "peak_source": peak_src,
-        "traffic_source": "ncu --set full (profiles/r1/ncu_final_details_transform_u8.txt): dram read 5.65 GB + write 26.16 GB per launch = 1.079 x the algorithmic 29.49 GB at 131,072 samples, scaled linearly to this launch",
+        "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.062), "peak_source": peak_src,
+        "traffic_source": "ncu --set full (profiles/r1/ncu_final_details_transform_u8.txt): dram read 5.16 GB + write 26.16 GB per launch = 1.062 x the algorithmic 29.49 GB at 131,072 samples, scaled linearly to this launch",
         "algorithmic_bytes_per_launch": ab["transform"], "ms_per_launch": tr_ms,
         "pack": {"kernel": "pack", "achieved": pack_gbs, "frac": pack_gbs / peak, "algorithmic_bytes_per_launch": ab["pack"], "ms_per_launch": pack_ms},
         "step": {"achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
