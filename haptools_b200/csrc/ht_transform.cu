@@ -472,6 +472,9 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
     const uintptr_t addr = reinterpret_cast<uintptr_t>(out);
     const int vec = ((addr | (uintptr_t)out_s_samp) & 15) == 0 ? 16
                     : ((addr | (uintptr_t)out_s_samp) & 1) == 0 ? 2 : 1;
+    if (quads4 && vec == 16 && transform_half_enabled())
+        return launch_transform_u8_half(planes, n_samples, n_keys, quad_off16, quads4, n_haps, out, out_s_samp, cnt,
+                                        (cudaStream_t)stream);
     // a grid holds at most 2^31-1 blocks: launch ranges of tile groups
     const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
     const int64_t tiles_per_launch = groups_per_launch * kTilesPerCta;

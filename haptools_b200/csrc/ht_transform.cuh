@@ -64,6 +64,12 @@ __device__ __forceinline__ void transpose32_dev(uint32_t (&a)[32]) {
     }
 }
 
+// half-tile form of the transform (ht_transform_half.cu); needs the planner's quads and 16-byte rows
+bool transform_half_enabled();
+int launch_transform_u8_half(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                             const uint32_t* quad_off16, const uint4* quads, int64_t n_haps, uint8_t* out,
+                             int64_t out_s_samp, unsigned long long* counts, cudaStream_t st);
+
 __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     uint4 o;
     o.x = spread4(bits & 15u);

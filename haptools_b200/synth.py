@@ -89,18 +89,20 @@ def synth_haplotype_refs(p: int, n_haps: int, seed: int, min_alleles: int = 2, m
     K = int(hap_off[-1])
     hap_of_ref = np.repeat(np.arange(n_haps), k)
     gaps = rng.integers(1, 5, size=K, dtype=np.int64)
+    nz = k > 0  # haplotypes without alleles (min_alleles=0) own no entries
     first = hap_off[:-1]
-    gaps[first] = 0
+    gaps[first[nz]] = 0
     csum = np.cumsum(gaps)
-    within = csum - csum[first][hap_of_ref]
-    span = within[hap_off[1:] - 1]  # offset of the last variant of each haplotype
+    within = csum - csum[np.minimum(first, max(K - 1, 0))][hap_of_ref] if K else csum
+    span = np.zeros(n_haps, dtype=np.int64)  # offset of the last variant of each haplotype
+    span[nz] = within[hap_off[1:][nz] - 1]
     start = (rng.random(n_haps) * (p - span)).astype(np.int64)
     ref_col = start[hap_of_ref] + within
     ref_allele = rng.integers(0, 2, size=K, dtype=np.int64)
     hap_label = rng.integers(0, n_pops, size=n_haps, dtype=np.int64) if n_pops else None
     if sort:
-        order = np.argsort(ref_col[hap_off[:-1]], kind="stable")
-        idx = np.concatenate([np.arange(hap_off[h], hap_off[h + 1]) for h in order])
+        order = np.argsort(start, kind="stable")
+        idx = np.concatenate([np.arange(hap_off[h], hap_off[h + 1]) for h in order] + [np.zeros(0, dtype=np.int64)])
         ref_col, ref_allele = ref_col[idx], ref_allele[idx]
         hap_off = np.concatenate([[0], np.cumsum(k[order])])
         if hap_label is not None:

@@ -1,0 +1,99 @@
+"""
+The two forms of the one-kernel transform -- half-tile (csrc/ht_transform_half.cu, the default when the
+planner's key quads are available) and tile (csrc/ht_transform.cu; HT_TRANSFORM_KERNEL=tile forces it)
+-- against the oracle: ragged row counts and haplotype groups, haplotypes without alleles, a block
+whose quads exceed the staging buffer (quads read from global memory), padded row pitch, fused counts.
+Bit-exact: np.array_equal on the 0/1 bytes.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import transform_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+from haptools_b200 import engine  # noqa: E402
+from haptools_b200.plan import plan_from_refs  # noqa: E402
+
+
+def _case(rng, n, p, H, max_k, long_hap=0):
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.02] = 255
+    k = rng.integers(0, min(max_k, p) + 1, size=H)
+    if long_hap:
+        k[H // 2] = min(long_hap, p)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, dtype=np.int64)])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    # make some haplotypes present: copy their alleles into a few samples
+    for h in rng.choice(H, size=min(H, 6), replace=False):
+        cols = ref_col[hap_off[h] : hap_off[h + 1]].astype(np.int64)
+        for s in rng.choice(n, size=min(n, 5), replace=False):
+            gt[s, cols, :] = ref_allele[hap_off[h] : hap_off[h + 1]][:, None]
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, None)
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    want = orc.transform_core(gt[:, ref_col.astype(np.int64)], ref_allele.astype(np.uint8), idxs, None, None)
+    return gt, plan, want
+
+
+SHAPES = [
+    # n, p, H, max_k, long_hap
+    (1, 8, 1, 3, 0), (31, 16, 7, 4, 0), (511, 24, 8, 5, 0), (512, 24, 9, 5, 0), (513, 24, 127, 5, 0),
+    (1024, 40, 128, 6, 0), (1537, 64, 129, 20, 0), (2504, 200, 300, 20, 0), (3000, 300, 137, 60, 0),
+    (2100, 4200, 40, 6, 4000), (700, 900, 260, 0, 0),
+]
+
+
+@pytest.mark.parametrize("kernel", ["half", "tile"])
+@pytest.mark.parametrize("n,p,H,max_k,long_hap", SHAPES)
+def test_transform_kernel_forms_vs_oracle(monkeypatch, kernel, n, p, H, max_k, long_hap):
+    monkeypatch.setenv("HT_TRANSFORM_KERNEL", kernel)
+    rng = np.random.default_rng(1000 * n + H)
+    gt, plan, want = _case(rng, n, p, H, max_k, long_hap)
+    dplan = engine.DevicePlan(plan)
+    gt_dev = torch.from_numpy(gt).cuda()
+    planes = engine.alloc_planes(n, plan.n_keys, gt_dev.device)
+    engine.pack(dplan, gt_dev.data_ptr(), gt_dev.stride(), n, planes)
+    want_counts = want.reshape(n, H, 2).sum(axis=(0, 2)).astype(np.int64)
+    for pitch in (engine.out_pitch(H), engine.out_pitch(H) + 48):
+        out = torch.full((n, pitch), 9, dtype=torch.uint8, device="cuda")
+        counts = torch.full((H,), -1, dtype=torch.int64, device="cuda")
+        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch, method="direct", counts=counts)
+        torch.cuda.synchronize()
+        got = out[:, : 2 * H].cpu().numpy().reshape(n, H, 2).view(np.bool_)
+        np.testing.assert_array_equal(got, want, err_msg=f"{kernel} pitch={pitch}")
+        np.testing.assert_array_equal(counts.cpu().numpy(), want_counts, err_msg=f"{kernel} counts")
+        # nothing is written beyond the 2H result bytes of a row
+        assert bool((out[:, 2 * H :] == 9).all()), f"{kernel}: bytes beyond 2H were written"
+
+
+def test_both_forms_agree_at_size():
+    """131,072 samples x 4,096 haplotypes of 2-20 alleles over 20 k keys: the two kernels bit for bit."""
+    import os
+
+    from haptools_b200 import synth
+
+    n, p, H = 131_072 + 777, 10_000, 4_096 + 8
+    plan = synth.synth_plan(p, H, seed=5)
+    dplan = engine.DevicePlan(plan)
+    planes = engine.alloc_planes(n, plan.n_keys, "cuda")
+    planes.random_(-(2**31), 2**31 - 1)
+    outs = []
+    old = os.environ.get("HT_TRANSFORM_KERNEL")
+    try:
+        for kernel in ("tile", "half"):
+            os.environ["HT_TRANSFORM_KERNEL"] = kernel
+            out = torch.empty((n, engine.out_pitch(H)), dtype=torch.uint8, device="cuda")
+            counts = torch.zeros(H, dtype=torch.int64, device="cuda")
+            engine.transform_u8(dplan, planes, n, out.data_ptr(), out.stride(0), method="direct", counts=counts)
+            torch.cuda.synchronize()
+            outs.append((out[:, : 2 * H], counts))
+    finally:
+        if old is None:
+            os.environ.pop("HT_TRANSFORM_KERNEL", None)
+        else:
+            os.environ["HT_TRANSFORM_KERNEL"] = old
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert int(outs[0][1].sum()) == int(outs[0][0].sum())
