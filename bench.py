@@ -440,9 +440,10 @@ def run_b200(args):
     tr_gbs = ab["transform"] / (tr_ms * 1e-3) / 1e9
     pack_gbs = ab["pack"] / (pack_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "transform_u8_kernel" if not two_phase else "and_local_bits_kernel + unpack_bits_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
-        "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.062), "peak_source": peak_src,
-        "traffic_source": "ncu --set full (profiles/r1/ncu_final_details_transform_u8.txt): dram read 5.16 GB + write 26.16 GB per launch = 1.062 x the algorithmic 29.49 GB at 131,072 samples, scaled linearly to this launch",
+        "bound": "hbm", "kernel": ("transform_u8_kernel" if os.environ.get("HT_TRANSFORM_KERNEL", "")[:1] == "t" else "transform_u8_half_kernel") if not two_phase else "and_local_bits_kernel + unpack_bits_u8_kernel", "achieved": tr_gbs, "peak": peak, "unit": "GB/s",
+        "frac": tr_gbs / peak, "traffic": int(ab["transform"] * 1.027), "peak_source": peak_src,
+        "traffic_source": "ncu --set full (profiles/r1/ncu_half_tile_details_transform_u8_half.txt): dram read 4.12 GB + write 26.16 GB per launch = 1.027 x the algorithmic 29.49 GB at 131,072 samples, scaled linearly to this launch",
+        "l2_note": "the kernel is bound by L2 throughput, not HBM: 37.1 GB of record reads + 26.2 GB of result writes cross L2<->SM per launch at 131,072 samples = 10.2 TB/s, against 9.2-9.3 TB/s for the same read:write mix with no arithmetic at all (profiles/micro/l2bw.cu, profiles/r1/micro_l2bw.txt)",
         "algorithmic_bytes_per_launch": ab["transform"], "ms_per_launch": tr_ms,
         "pack": {"kernel": "pack", "achieved": pack_gbs, "frac": pack_gbs / peak, "algorithmic_bytes_per_launch": ab["pack"], "ms_per_launch": pack_ms},
         "step": {"achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
