@@ -22,6 +22,8 @@
 //                  bits bytewise, then byte-transposes with PRMT (details at the kernel)
 //
 // Roofline: HBM read of n*V*2 genotype bytes (+ ancestry) and write of A*2*ceil(n/32)*4.
+#include <cstdlib>
+
 #include "ht_common.cuh"
 
 namespace ht {
@@ -1055,6 +1057,227 @@ pack_sm2_anc_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Line-consuming form of pack_sm2_anc_kernel: warp = 4 words x the CTA's 64 columns, so that one load
+// instruction reads 4 rows x 128 contiguous bytes (whole cache lines: no line waits in L2 for the other
+// three warps that own a sector of it); lane = one word x 8 columns as before.  The price: a key's
+// record is stored 4 words (32 bytes, one sector) per store instruction instead of 16.  All warps of a
+// CTA share the same 64 columns: key ranges and (allele, label) bytes are staged once per CTA.  The
+// allele-1 accumulators are parked in shared memory like the label bits and the key loop is rolled
+// (93 registers).  Default form for ancestry plans: 18.0 ms against 19.7 ms on the ancestry config
+// (0.74 of the measured HBM peak); 3 CTAs per SM (80 registers) are SLOWER (22.9 ms), see DESIGN.md.
+// -----------------------------------------------------------------------------------------
+constexpr int kAncLineKeyStage = 1024;  // staged (allele, label) pairs per CTA (its 64 columns)
+constexpr size_t kSm2AncLineSmem = sizeof(uint32_t) * 64 * kPackThreads + sizeof(int2) * kSm2CtaCols +
+                                   sizeof(uint16_t) * kAncLineKeyStage + sizeof(int) * 2;
+
+#ifndef HT_ANC_LINE_MIN_CTAS
+#define HT_ANC_LINE_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(kPackThreads, HT_ANC_LINE_MIN_CTAS)
+pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* gl = s_dyn + threadIdx.x;  // [(q * 4 + plane) * 4 + j][thread]; plane 0 = allele 1, 1..3 = label bits
+    int2* s_kr = reinterpret_cast<int2*>(s_dyn + 64 * kPackThreads);  // key range of each of the CTA's 64 columns
+    uint16_t* s_ki = reinterpret_cast<uint16_t*>(s_kr + kSm2CtaCols);
+    int* s_span = reinterpret_cast<int*>(s_ki + kAncLineKeyStage);     // {first key, end key} of the CTA
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = tile0 + blockIdx.x / n_cblocks;
+    const int word = warp * 4 + (lane >> 3);
+    const int64_t wcol0 = (cblock0 + blockIdx.x % n_cblocks) * kSm2CtaCols;  // the CTA's first column
+    if (wcol0 >= a.n_cols) return;  // CTA-uniform
+    const int64_t col0 = wcol0 + (lane & 7) * 8;
+    const int ncols = (int)max((int64_t)0, min((int64_t)8, a.n_cols - col0));
+    const int64_t s0 = tile * kTileSamples + 32 * word;
+    const int nrows = (int)max((int64_t)0, min((int64_t)32, a.n - s0));
+    const bool have_rows = ncols > 0 && nrows > 0;
+    const bool full = nrows == 32 && ncols == 8;
+    int2* my_kr = s_kr;
+    uint16_t* my_ki = s_ki;
+
+    // (1) key ranges of the CTA's 64 columns (threads 0..63 fetch one each)
+    int2 kr = make_int2(0, 0);
+    if (threadIdx.x < kSm2CtaCols && wcol0 + threadIdx.x < a.n_cols)
+        kr = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + threadIdx.x);
+    if (threadIdx.x == 0) {
+        s_span[0] = 0x7fffffff;
+        s_span[1] = 0;
+    }
+    __syncthreads();
+
+    // (2) genotype rows -> 8-row block accumulators of the allele-1 plane, parked in thread-private shared
+    //     memory like those of the label bits below: registers are the load buffers, nothing else stays live
+    uint32_t d = 0u;
+    const uint8_t* gbase = a.gt + s0 * a.gs + col0 * 2;
+    const uint8_t* lbase = a.anc + s0 * a.as + col0 * 2;
+    if (have_rows) {
+        const uint8_t* p = gbase;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint4 x[8];
+            if (full) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.gs) {
+                    x[rr] = make_uint4(0u, 0u, 0u, 0u);
+                    if (8 * q + rr < nrows) x[rr] = load_row16(p, ncols);
+                }
+            }
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+            for (int rr = 7; rr >= 0; --rr) {
+                a0 = (a0 << 1) + (x[rr].x & 0x01010101u);
+                a1 = (a1 << 1) + (x[rr].y & 0x01010101u);
+                a2 = (a2 << 1) + (x[rr].z & 0x01010101u);
+                a3 = (a3 << 1) + (x[rr].w & 0x01010101u);
+                d |= ((x[rr].x | x[rr].y) | (x[rr].z | x[rr].w)) & 0xfefefefeu;
+            }
+            uint32_t* dst = gl + (q * 16) * kPackThreads;
+            dst[0] = a0;
+            dst[kPackThreads] = a1;
+            dst[2 * kPackThreads] = a2;
+            dst[3 * kPackThreads] = a3;
+        }
+    }
+
+    // (3) publish the key ranges, find the CTA's key span, fetch its (allele, label) bytes
+    if (threadIdx.x < kSm2CtaCols) {
+        s_kr[threadIdx.x] = kr;
+        if (kr.y > 0) {
+            atomicMin(&s_span[0], kr.x);
+            atomicMax(&s_span[1], kr.x + kr.y);
+        }
+    }
+    __syncthreads();
+    const int kmin = s_span[0], kmax = s_span[1];
+    if (kmax <= kmin) return;  // none of the CTA's columns is referenced (CTA-uniform)
+    const int n_k = kmax - kmin;
+    const bool ki_staged = n_k <= kAncLineKeyStage;
+    uint32_t ki_reg[kAncLineKeyStage / kPackThreads];
+#pragma unroll
+    for (int t = 0; t < kAncLineKeyStage / kPackThreads; ++t) {
+        const int idx = threadIdx.x + kPackThreads * t;
+        ki_reg[t] = 0u;
+        if (ki_staged && idx < n_k)
+            ki_reg[t] = (uint32_t)__ldg(a.key_allele + kmin + idx) | ((uint32_t)__ldg(a.key_label + kmin + idx) << 8);
+    }
+
+    // (4) ancestry rows -> block accumulators of label bits 0..2, parked in shared memory
+    if (have_rows) {
+        const uint8_t* p = lbase;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint4 c[8];
+            if (full) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.as) c[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr, p += a.as) {
+                    c[rr] = make_uint4(0u, 0u, 0u, 0u);
+                    if (8 * q + rr < nrows) c[rr] = load_row16(p, ncols);
+                }
+            }
+#pragma unroll
+            for (int bit = 0; bit < 3; ++bit) {
+                uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+                for (int rr = 7; rr >= 0; --rr) {
+                    a0 = (a0 << 1) + ((c[rr].x >> bit) & 0x01010101u);
+                    a1 = (a1 << 1) + ((c[rr].y >> bit) & 0x01010101u);
+                    a2 = (a2 << 1) + ((c[rr].z >> bit) & 0x01010101u);
+                    a3 = (a3 << 1) + ((c[rr].w >> bit) & 0x01010101u);
+                }
+                uint32_t* dst = gl + ((q * 4 + bit + 1) * 4) * kPackThreads;
+                dst[0] = a0;
+                dst[kPackThreads] = a1;
+                dst[2 * kPackThreads] = a2;
+                dst[3 * kPackThreads] = a3;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) d |= ((c[rr].x | c[rr].y) | (c[rr].z | c[rr].w)) & 0xf8f8f8f8u;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i) gl[i * kPackThreads] = 0u;
+    }
+
+    // (5) publish the key bytes
+    if (ki_staged) {
+#pragma unroll
+        for (int t = 0; t < kAncLineKeyStage / kPackThreads; ++t)
+            if (threadIdx.x + kPackThreads * t < n_k) my_ki[threadIdx.x + kPackThreads * t] = (uint16_t)ki_reg[t];
+    }
+    __syncthreads();
+
+    // (6) every key of my 8 columns, one pair of columns (= one 4-byte word of my rows) at a time:
+    //     combine the planes, store word `word` of both strands.  The loop is rolled and nothing but the
+    //     shared-memory accumulators is carried into it.
+    if (ncols <= 0) return;
+    const uint32_t vm = valid_mask(a.n, tile, word);
+    uint32_t fl = 0u;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        uint32_t Wj[4], L[3][4], Zj[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int plane = 0; plane < 4; ++plane) {
+            uint32_t G[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) G[q] = gl[((q * 4 + plane) * 4 + j) * kPackThreads];
+            if (plane == 0) byte_transpose4(G, Wj);
+            else byte_transpose4(G, L[plane - 1]);
+        }
+        if (d) {
+            // invalid plane (GT byte >= 2 or label byte >= 8), only for lanes that saw such a byte: a
+            // second read of my rows' word j (L1/L2 hits), one row at a time
+            const int c_lo = (lane & 7) * 8 + 2 * j;
+            const uint32_t refmask = (my_kr[c_lo].y > 0 ? 0x0000ffffu : 0u) | (my_kr[c_lo + 1].y > 0 ? 0xffff0000u : 0u);
+            const int nc = ncols - 2 * j;  // columns of this word that exist (may be <= 0)
+            const uint8_t* pg = gbase + 4 * j;
+            const uint8_t* pl = lbase + 4 * j;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                uint32_t z = 0u;
+#pragma unroll 1
+                for (int rr = 0; rr < 8; ++rr, pg += a.gs, pl += a.as) {  // row rr enters at bit 7, ends at bit rr
+                    uint32_t x = 0u, c = 0u;
+                    if (8 * q + rr < nrows && nc > 0) {
+                        x = load_cols4(pg, nc);
+                        c = load_cols4(pl, nc);
+                    }
+                    z = (z >> 1) | nz_bytes_msb((x & 0xfefefefeu) | (c & 0xf8f8f8f8u));
+                    if (a.flags) fl |= qc_flags4(x & refmask);
+                }
+                insert_bytes(Zj, z, q);
+            }
+        }
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+            const int2 r = my_kr[(lane & 7) * 8 + 2 * j + cp];
+#pragma unroll 1
+            for (int t = 0; t < r.y; ++t) {
+                const int key = r.x + t;
+                const uint32_t info = ki_staged ? (uint32_t)my_ki[key - kmin]
+                                                : ((uint32_t)__ldg(a.key_allele + key) | ((uint32_t)__ldg(a.key_label + key) << 8));
+                const uint32_t mA = (info & 1u) ? 0u : 0xffffffffu, m0 = (info & 0x100u) ? 0u : 0xffffffffu;
+                const uint32_t m1 = (info & 0x200u) ? 0u : 0xffffffffu, m2 = (info & 0x400u) ? 0u : 0xffffffffu;
+                uint2 o;
+                o.x = (Wj[2 * cp] ^ mA) & (L[0][2 * cp] ^ m0) & (L[1][2 * cp] ^ m1) & (L[2][2 * cp] ^ m2) &
+                      ~Zj[2 * cp] & vm;
+                o.y = (Wj[2 * cp + 1] ^ mA) & (L[0][2 * cp + 1] ^ m0) & (L[1][2 * cp + 1] ^ m1) &
+                      (L[2][2 * cp + 1] ^ m2) & ~Zj[2 * cp + 1] & vm;
+                record(a, tile, (uint32_t)key)[word] = o;
+            }
+        }
+    }
+    if (a.flags && fl) {
+        if (fl & ~*reinterpret_cast<volatile uint32_t*>(a.flags)) atomicOr(a.flags, fl);
+    }
+}
+
 static bool aligned(const void* p, int64_t stride, int to) {
     return ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)stride) & (uintptr_t)(to - 1)) == 0;
 }
@@ -1174,7 +1397,10 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                 return HT_ERR_UNSUPPORTED;
             }
             const int64_t n_cblocks = (n_cols + kSm2CtaCols - 1) / kSm2CtaCols;
-            if (int rc = anc ? launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem)
+            const char* anc_form = getenv("HT_PACK_ANC_KERNEL");  // "warp" = pack_sm2_anc_kernel (A/B measurements, tests)
+            const bool anc_line = !(anc_form && anc_form[0] == 'w');
+            if (int rc = anc ? (anc_line ? launch_tiled(pack_sm2_anc_line_kernel, a, n_cblocks, 0, true, st, kSm2AncLineSmem)
+                                         : launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem))
                              : launch_tiled(pack_sm2_kernel, a, n_cblocks, 0, true, st))
                 return rc;
             if (t->n_var_other > 0) {  // the few variants with other keys: generic kernel

@@ -97,3 +97,32 @@ def test_both_forms_agree_at_size():
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
     assert int(outs[0][1].sum()) == int(outs[0][0].sum())
+
+
+@pytest.mark.parametrize("form", ["line", "warp"])
+@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1032, 40, 70), (2504, 64, 200), (3104, 200, 333), (1025, 1000, 400)])
+def test_ancestry_pack_forms_vs_oracle(monkeypatch, form, n, p, H):
+    """Both forms of the sample-major ancestry pack (csrc/ht_pack.cu: pack_sm2_anc_line_kernel, the default,
+    and pack_sm2_anc_kernel) against the oracle, with missing calls and labels >= 8 in the data."""
+    monkeypatch.setenv("HT_PACK_ANC_KERNEL", form)
+    from haptools_b200 import _cuda
+
+    rng = np.random.default_rng(77 * n + H)
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.01] = 255
+    anc = np.ascontiguousarray(np.repeat(rng.integers(0, 5, size=(n, (p + 6) // 7, 2), dtype=np.uint8), 7, axis=1)[:, :p])
+    anc[rng.random((n, p, 2)) < 0.002] = 9  # a label no haplotype asks for, outside the 3-bit planes
+    k = rng.integers(0, min(6, p) + 1, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, dtype=np.int64)])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    hap_label = rng.integers(0, 5, size=H)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, np.repeat(hap_label, k))
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    cols = ref_col.astype(np.int64)
+    want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs, anc[:, cols], hap_label.astype(np.uint8))
+    dplan = engine.DevicePlan(plan)
+    out = engine.transform_device(torch.from_numpy(gt).cuda(), dplan, ancestry=torch.from_numpy(anc).cuda(),
+                                  pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC if p % 8 == 0 else _cuda.HT_PACK_AUTO)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=form)
