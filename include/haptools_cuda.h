@@ -75,7 +75,10 @@ extern "C" {
                                    builds the planes of every allele-0/1 key with 128-byte
                                    coalesced record stores; variants listed in
                                    tables->var_other go through the generic kernel.  What
-                                   HT_PACK_AUTO picks when it can.                         */
+                                   HT_PACK_AUTO picks when it can.  With ancestry the
+                                   line-consuming form runs (a warp reads 4 rows x 128 bytes,
+                                   32-byte record stores); HT_PACK_ANC_KERNEL=warp in the
+                                   environment selects the earlier form (measurements, tests) */
 
 /* direction of ht_copy2d */
 #define HT_COPY_H2D 1
@@ -172,8 +175,14 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
  *           quads of 4 by repeating its last key, entries = key * 256 (byte offset of the record
  *           inside a tile), low bits of a quad's first entry = flags (1: last quad of its
  *           haplotype, 2: haplotype without alleles), quad_off16[g] = first quad of haplotypes
- *           16 g .. 16 g + 15 (haptools_b200/plan.py quad_tables).  Without them the kernel
- *           builds the quads from the CSR in every CTA (15-20 % slower at UKB scale).
+ *           16 g .. 16 g + 15 (haptools_b200/plan.py quad_tables).  With them, and with `out` and
+ *           `out_s_samp` multiples of 16, the half-tile kernel runs (csrc/ht_transform_half.cu:
+ *           512 samples x 128 haplotypes per CTA); without them the tile kernel builds the quads
+ *           from the CSR in every CTA (15-20 % slower at UKB scale).  Same result bytes either
+ *           way.  Environment (measurements and tests only): HT_TRANSFORM_KERNEL=tile forces the
+ *           tile kernel.  The first call on a device makes the L2 policy word the half-tile
+ *           kernel takes (a one-thread kernel and a stream synchronize, once per process and
+ *           device): capture CUDA graphs after one eager call.
  *   out     uint8 matrix: element (s, h, c) at out + s*out_s_samp + 2*h + c receives exactly
  *           0x00 or 0x01 (numpy bool bytes).  A haplotype without keys yields 0x01
  *           (np.all over an empty axis).  out_s_samp >= 2*H.  Rows >= n_samples are not
