@@ -58,6 +58,10 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
         case HT_COPY_D2D: k = cudaMemcpyDeviceToDevice; break;
         default: return ht::bad_arg("ht_copy2d: unknown kind");
     }
+    if (dst_pitch == width_bytes && src_pitch == width_bytes) {  // dense on both sides: one linear copy
+        HT_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)width_bytes * (size_t)height, k, (cudaStream_t)stream));
+        return HT_OK;
+    }
     HT_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch,
                                   (size_t)width_bytes, (size_t)height, k,
                                   (cudaStream_t)stream));

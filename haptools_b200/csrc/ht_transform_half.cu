@@ -26,6 +26,7 @@
 //      instruction writes 2 x 256 contiguous bytes (st.global.cs.v4).
 //
 // Algorithmic bytes are those of the tile form: planes read once, n*H*2 result bytes written.
+#include <atomic>
 #include <cstdlib>
 
 #include "ht_transform.cuh"
@@ -320,16 +321,24 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
     }
 }
 
-// evict_last policy word of the current device (made once per device and process)
+// evict_last policy word of the current device (made once per device and process; 0 = not made yet:
+// createpolicy never returns 0 for evict_last -- and if it did the word would just be made again)
 static int l2_policy(uint64_t* pol, cudaStream_t st) {
     constexpr int kMaxDev = 64;
-    static uint64_t cache[kMaxDev];
-    static bool have[kMaxDev];
+    static std::atomic<uint64_t> cache[kMaxDev];
     int dev = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < kMaxDev && have[dev]) {
-        *pol = cache[dev];
-        return HT_OK;
+    if (dev >= 0 && dev < kMaxDev) {
+        const uint64_t v = cache[dev].load(std::memory_order_acquire);
+        if (v) {
+            *pol = v;
+            return HT_OK;
+        }
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+        set_error("ht_transform_u8: call once eagerly on this device before capturing it in a CUDA graph");
+        return HT_ERR_UNSUPPORTED;
     }
     uint64_t* d = nullptr;
     HT_CUDA_TRY(cudaMalloc(&d, sizeof(uint64_t)));
@@ -338,10 +347,7 @@ static int l2_policy(uint64_t* pol, cudaStream_t st) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     if (e != cudaSuccess) return cuda_fail(e, "make_policy_kernel");
-    if (dev >= 0 && dev < kMaxDev) {
-        cache[dev] = *pol;
-        have[dev] = true;  // benign race: every thread computes the same word
-    }
+    if (dev >= 0 && dev < kMaxDev) cache[dev].store(*pol, std::memory_order_release);
     return HT_OK;
 }
 

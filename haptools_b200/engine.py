@@ -368,6 +368,23 @@ def default_chunk(n: int, p: int, n_haps: int, target_bytes: int = 512 << 20) ->
     return int(min(max(n, 1), rows))
 
 
+def _ramped_bounds(n: int, chunk: int, n_devs: int = 1):
+    """Sample ranges of at most `chunk` samples, the first ones of every device short (chunk/8, chunk/4,
+    chunk/2): the result's D2H stream -- the bound of the host pipeline -- can only start when the first
+    chunk has been uploaded and transformed, so the lead-in is one SHORT upload instead of a full one."""
+    bounds, s = [], 0
+    for div in (8, 4, 2):
+        size = max(256, chunk // div // 256 * 256)
+        for _ in range(n_devs):
+            if s < n and n - s > size:
+                bounds.append((s, s + size))
+                s += size
+    while s < n:
+        bounds.append((s, min(n, s + chunk)))
+        s += chunk
+    return bounds
+
+
 def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
     """A page-locked numpy array (owned by a torch pinned tensor kept alive through .base)."""
     require_cuda()
@@ -387,7 +404,7 @@ class _HostPipe:
             self.dplan = dplan if dplan is not None and dplan.device == dev else device_plan(plan, dev)
             self.nbuf = nbuf = min(2, len(bounds))
             self.pitch = out_pitch(H)
-            ends = bounds[:1] + bounds[-1:]
+            ends = sorted(bounds, key=lambda b: b[0] - b[1])[:2] + bounds[-1:]  # the largest chunks (and the last)
             gt_bytes = max(_region(gt, *b).dev_bytes() for b in ends)
             self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.anc_buf = [None] * nbuf
@@ -514,7 +531,7 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
     if len(devs) > 1 and not chunk_samples:  # at least two chunks per device keep its three streams busy
         chunk = min(chunk, max(TILE, -(-n // (2 * len(devs))) // TILE * TILE))
     chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
-    bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+    bounds = _ramped_bounds(n, chunk, len(devs)) if not chunk_samples else [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
     devs = devs[: len(bounds)]
     pipes = [_HostPipe(d, plan, dplan, gt, ancestry, bounds[i :: len(devs)], chunk, pack_mode, out, H)
              for i, d in enumerate(devs)]

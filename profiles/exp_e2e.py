@@ -8,7 +8,7 @@ dplan = engine.DevicePlan(plan)
 host_gt = engine.pinned_empty((ne, p, 2))
 host_gt[:] = synth.synth_gt(256, p, 3, mode=1)[np.arange(ne) % 256]
 host_out = engine.pinned_empty((ne, H, 2))
-for chunk in (1024, 2048, 4096, 8192, 16384):
+for chunk in (None, 512, 1024, 2048, 4096, 16384):  # None = the default schedule (ramped lead-in)
     for _ in range(2):
         engine.transform_host(host_gt, plan, out=host_out, dplan=dplan, chunk_samples=chunk)
     ts = []
@@ -17,4 +17,4 @@ for chunk in (1024, 2048, 4096, 8192, 16384):
         engine.transform_host(host_gt, plan, out=host_out, dplan=dplan, chunk_samples=chunk)
         torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
     dt = min(ts)
-    print(f"chunk {chunk:6d}: {dt*1e3:7.2f} ms  {ne*H*2/dt:.3e} calls/s  H2D+D2H {(host_gt.nbytes+host_out.nbytes)/dt/1e9:.1f} GB/s")
+    print(f"chunk {str(chunk):>6s}: {dt*1e3:7.2f} ms  {ne*H*2/dt:.3e} calls/s  H2D+D2H {(host_gt.nbytes+host_out.nbytes)/dt/1e9:.1f} GB/s")

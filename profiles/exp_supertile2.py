@@ -22,8 +22,9 @@ def whole():
     engine.transform_u8(dp, planes, n, out.data_ptr(), 2 * H)
 ms = timeit(whole); print(f"whole: {ms:.2f} ms")
 ref = out.clone()
-sp, st = torch.cuda.Stream(), torch.cuda.Stream()
-for S, prio in ((4, 0), (8, 0), (16, 0), (32, 0)):
+for S, prio in ((8, 0), (16, 0), (32, 0), (8, -1), (16, -1), (32, -1), (16, 1), (32, 1)):
+    # prio -1: the pack stream has priority (its CTAs are scheduled first whenever a slot frees); +1: the transform stream
+    sp, st = torch.cuda.Stream(priority=min(prio, 0)), torch.cuda.Stream(priority=min(-prio, 0))
     rows = S * 1024
     NB = 3
     pl = [engine.alloc_planes(rows, plan.n_keys, dev) for _ in range(NB)]
@@ -42,4 +43,4 @@ for S, prio in ((4, 0), (8, 0), (16, 0), (32, 0)):
         cur.wait_stream(sp); cur.wait_stream(st)
     out.zero_()
     ms = timeit(piped)
-    print(f"S={S}: {ms:.2f} ms  equal={torch.equal(out, ref)}")
+    print(f"S={S} prio={prio}: {ms:.2f} ms  equal={torch.equal(out, ref)}", flush=True)
