@@ -190,11 +190,26 @@ struct VmItem {
     uint32_t kb, ke;        // the variant's keys
 };
 
+// column and key range of a variant: fetched TWO items ahead of the arithmetic, so that the row loads of
+// the next item (one ahead) never wait for their own address (a warp issues in order: it would sit out
+// an L2 round trip at the first use of `col` before it could even start on the current item)
+struct VmIdx {
+    uint32_t col, kb, ke;
+};
+
+__device__ __forceinline__ VmIdx vm_fetch_idx(const PackArgs& a, int64_t v) {
+    VmIdx ix;
+    ix.col = __ldg(a.var_col + v);
+    ix.kb = __ldg(a.var_key_off + v);
+    ix.ke = __ldg(a.var_key_off + v + 1);
+    return ix;
+}
+
 template <bool kAnc>
-__device__ __forceinline__ void vm_fetch(const PackArgs& a, int64_t tile, int64_t v, int lane, VmItem<kAnc>& it) {
-    const uint32_t col = __ldg(a.var_col + v);
-    it.kb = __ldg(a.var_key_off + v);
-    it.ke = __ldg(a.var_key_off + v + 1);
+__device__ __forceinline__ void vm_fetch(const PackArgs& a, int64_t tile, const VmIdx& ix, int lane, VmItem<kAnc>& it) {
+    const uint32_t col = ix.col;
+    it.kb = ix.kb;
+    it.ke = ix.ke;
     const int rows = (int)min((int64_t)kTileSamples, a.n - tile * kTileSamples);
     const uint8_t* g = a.gt + (int64_t)col * a.gv + tile * (2 * kTileSamples);
     const uint8_t* l = kAnc ? a.anc + (int64_t)col * a.av + tile * (2 * kTileSamples) : nullptr;
@@ -321,19 +336,31 @@ pack_vm_kernel(const PackArgs a, int64_t n_tiles) {
     const int64_t step_t = stride / a.n_vars, step_v = stride % a.n_vars;
     int64_t tile = item / a.n_vars, v = item % a.n_vars;
     VmItem<kAnc> cur, nxt;
-    vm_fetch<kAnc>(a, tile, v, lane, cur);
+    vm_fetch<kAnc>(a, tile, vm_fetch_idx(a, v), lane, cur);
+    // (tile, variant) of the next item, and the index entries of that item (in flight since one iteration)
+    int64_t tile_n = tile + step_t, v_n = v + step_v;
+    if (v_n >= a.n_vars) {
+        v_n -= a.n_vars;
+        ++tile_n;
+    }
+    VmIdx ix_n = {0u, 0u, 0u};
+    if (item + stride < n_items) ix_n = vm_fetch_idx(a, v_n);
 #pragma unroll 1
     for (; item < n_items; item += stride) {
-        int64_t tile_n = tile + step_t, v_n = v + step_v;
-        if (v_n >= a.n_vars) {
-            v_n -= a.n_vars;
-            ++tile_n;
+        int64_t tile_nn = tile_n + step_t, v_nn = v_n + step_v;
+        if (v_nn >= a.n_vars) {
+            v_nn -= a.n_vars;
+            ++tile_nn;
         }
-        if (item + stride < n_items) vm_fetch<kAnc>(a, tile_n, v_n, lane, nxt);
+        VmIdx ix_nn = {0u, 0u, 0u};
+        if (item + stride < n_items) vm_fetch<kAnc>(a, tile_n, ix_n, lane, nxt);
+        if (item + 2 * stride < n_items) ix_nn = vm_fetch_idx(a, v_nn);
         pack_vm_item<kAnc>(a, tile, cur, lane);
         cur = nxt;
         tile = tile_n;
-        v = v_n;
+        tile_n = tile_nn;
+        v_n = v_nn;
+        ix_n = ix_nn;
     }
 }
 

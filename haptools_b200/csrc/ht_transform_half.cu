@@ -310,6 +310,11 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
             if (sl >= rows) continue;
             uint8_t* p = p0 + (int64_t)(slot_sample(m) + 4 * u) * out_s_samp;
             const uint32_t V = W >> (4 * u);
+            if (n_my_haps == 8) {  // last rows of the matrix, full group: still one 16-byte store per row
+                st_stream_v4(p, make_uint4(V & 0x01010101u, (V >> 1) & 0x01010101u, (V >> 2) & 0x01010101u,
+                                           (V >> 3) & 0x01010101u));
+                continue;
+            }
             for (int q = 0; q < n_my_haps; ++q) {
                 // bytes 2q, 2q+1 of the piece: byte i sits at bit 8 * (i & 3) + (i >> 2)
                 const int i0 = 2 * q, i1 = 2 * q + 1;
