@@ -2,6 +2,12 @@
 // few host<->device copy helpers.  See include/haptools_cuda.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "ht_common.cuh"
 
@@ -24,6 +30,109 @@ int cuda_fail(cudaError_t err, const char* what) {
 int bad_arg(const char* what) {
     set_error("bad argument: %s", what);
     return HT_ERR_BAD_ARG;
+}
+
+// ---------------------------------------------------------------------------------------
+// Upload from PAGEABLE host memory (what `gts.data` is when it comes out of cyvcf2 / pgenlib /
+// numpy).  cudaMemcpy2DAsync stages such a source through the driver's own bounce buffer with one
+// host thread (11 GB/s on the B200 box); here a few host threads copy row blocks into a ring of
+// page-locked bounce buffers and every block leaves with an asynchronous DMA, so the upload runs
+// at what memcpy on several cores and the PCIe link deliver (HT_HOST_COPY_THREADS, default 4; every
+// thread owns two 8 MB bounce buffers and whole row blocks).  Pure data movement: no byte is
+// interpreted on the host.
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxCopyThreads = 8, kBufsPerThread = 2;
+constexpr size_t kBounceBytes = 8u << 20;
+struct Bounce {
+    std::mutex mu;  // one staged upload at a time per process
+    uint8_t* buf[kMaxCopyThreads][kBufsPerThread] = {};
+    cudaEvent_t ev[kMaxCopyThreads][kBufsPerThread] = {};
+    bool used[kMaxCopyThreads][kBufsPerThread] = {};
+    int dev = -1;
+};
+Bounce g_bounce;
+
+int host_threads() {
+    static const int n = [] {
+        const char* e = getenv("HT_HOST_COPY_THREADS");
+        int v = e ? atoi(e) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && v > hw) v = hw;
+        return v < 1 ? 1 : (v > kMaxCopyThreads ? kMaxCopyThreads : v);
+    }();
+    return n;
+}
+
+// worker t of nt: row blocks t, t + nt, ... through its own pair of bounce buffers
+void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, const uint8_t* src, int64_t src_pitch,
+                   int64_t width, int64_t height, int64_t rows_per_block, cudaStream_t st, cudaError_t* err) {
+    cudaError_t e = t ? cudaSetDevice(dev) : cudaSuccess;  // a new host thread starts on device 0
+    int b = 0;
+    for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
+        const int64_t rows = height - r0 < rows_per_block ? height - r0 : rows_per_block;
+        if (g_bounce.used[t][b]) e = cudaEventSynchronize(g_bounce.ev[t][b]);  // its last DMA has left
+        if (e != cudaSuccess) break;
+        uint8_t* stage = g_bounce.buf[t][b];
+        const uint8_t* s = src + r0 * src_pitch;
+        if (src_pitch == width) {
+            memcpy(stage, s, (size_t)(rows * width));
+        } else {
+            for (int64_t r = 0; r < rows; ++r) memcpy(stage + r * width, s + r * src_pitch, (size_t)width);
+        }
+        e = cudaMemcpy2DAsync(dst + r0 * dst_pitch, (size_t)dst_pitch, stage, (size_t)width, (size_t)width, (size_t)rows,
+                              cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[t][b], st);
+        g_bounce.used[t][b] = e == cudaSuccess;
+    }
+    *err = e;
+}
+}  // namespace
+
+static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                             int64_t height, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_bounce.mu);
+    int dev = 0;
+    HT_CUDA_TRY(cudaGetDevice(&dev));
+    const int64_t rows_per_block = (int64_t)(kBounceBytes / (size_t)width);
+    const int64_t n_blocks = (height + rows_per_block - 1) / rows_per_block;
+    const int nt = (int)(n_blocks < host_threads() ? n_blocks : host_threads());
+    for (int t = 0; t < nt; ++t) {
+        for (int b = 0; b < kBufsPerThread; ++b) {
+            if (!g_bounce.buf[t][b])
+                HT_CUDA_TRY(cudaHostAlloc((void**)&g_bounce.buf[t][b], kBounceBytes, cudaHostAllocPortable));
+            if (g_bounce.ev[t][b] && g_bounce.dev != dev) {  // events belong to a device: remake them after a switch
+                if (g_bounce.used[t][b]) cudaEventSynchronize(g_bounce.ev[t][b]);
+                cudaEventDestroy(g_bounce.ev[t][b]);
+                g_bounce.ev[t][b] = nullptr;
+                g_bounce.used[t][b] = false;
+            }
+            if (!g_bounce.ev[t][b]) HT_CUDA_TRY(cudaEventCreateWithFlags(&g_bounce.ev[t][b], cudaEventDisableTiming));
+        }
+    }
+    if (g_bounce.dev != dev) {  // buffers of threads not used this time: drop their stale events too
+        for (int t = nt; t < kMaxCopyThreads; ++t)
+            for (int b = 0; b < kBufsPerThread; ++b)
+                if (g_bounce.ev[t][b]) {
+                    if (g_bounce.used[t][b]) cudaEventSynchronize(g_bounce.ev[t][b]);
+                    cudaEventDestroy(g_bounce.ev[t][b]);
+                    g_bounce.ev[t][b] = nullptr;
+                    g_bounce.used[t][b] = false;
+                }
+    }
+    g_bounce.dev = dev;
+    cudaError_t errs[kMaxCopyThreads];
+    std::vector<std::thread> th;
+    th.reserve(nt > 1 ? nt - 1 : 0);
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    for (int t = 1; t < nt; ++t)
+        th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[t]);
+    upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[0]);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+        if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "staged upload from pageable memory");
+    return HT_OK;
 }
 
 }  // namespace ht
@@ -57,6 +166,13 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
         case HT_COPY_D2H: k = cudaMemcpyDeviceToHost; break;
         case HT_COPY_D2D: k = cudaMemcpyDeviceToDevice; break;
         default: return ht::bad_arg("ht_copy2d: unknown kind");
+    }
+    if (kind == HT_COPY_H2D && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes) {
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, src);
+        if (e != cudaSuccess) cudaGetLastError();  // old drivers report unregistered memory as an error
+        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered)
+            return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream);
     }
     if (dst_pitch == width_bytes && src_pitch == width_bytes) {  // dense on both sides: one linear copy
         HT_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)width_bytes * (size_t)height, k, (cudaStream_t)stream));
