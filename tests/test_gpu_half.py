@@ -126,3 +126,25 @@ def test_ancestry_pack_forms_vs_oracle(monkeypatch, form, n, p, H):
                                   pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC if p % 8 == 0 else _cuda.HT_PACK_AUTO)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=form)
+
+
+@pytest.mark.parametrize("layout", ["C", "C3", "F"])
+def test_pageable_upload_through_bounce_buffers(layout):
+    """Host arrays in PAGEABLE memory of more than 4 MB take ht_copy2d's own staged upload (host threads
+    + page-locked bounce buffers, csrc/ht_capi.cu): dense rows, rows with a phase column in between (pitch >
+    width), and the variant-major view of the VCF reader; several chunks, several blocks per chunk."""
+    n, p, H = 20_000, 600, 64
+    rng = np.random.default_rng(3)
+    gt, plan, want = _case(rng, n, p, H, 5)
+    if layout == "C":
+        arr = gt  # 24 MB, dense
+    elif layout == "C3":
+        c3 = np.ones((n, p, 3), dtype=np.uint8)
+        c3[:, :, :2] = gt
+        arr = c3[:, :, :2]
+    else:
+        arr = np.ascontiguousarray(gt.transpose(1, 0, 2)).transpose(1, 0, 2)
+    got = engine.transform_host(arr, plan, chunk_samples=8192)
+    np.testing.assert_array_equal(got, want)
+    got = engine.transform_host(arr, plan)
+    np.testing.assert_array_equal(got, want)
