@@ -148,3 +148,28 @@ def test_pageable_upload_through_bounce_buffers(layout):
     np.testing.assert_array_equal(got, want)
     got = engine.transform_host(arr, plan)
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_both_forms(monkeypatch, seed):
+    """Random shapes around the kernels' boundaries (512-sample half tiles, groups of 8 / 16 / 128
+    haplotypes, staging capacity) through both transform kernels, against the oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([1, 7, 511, 512, 513, 1023, 1024, 1025, 1535, 2047, 2049, 2560, 3071])) + int(rng.integers(0, 3))
+    H = int(rng.choice([1, 7, 8, 9, 15, 16, 17, 127, 128, 129, 255, 257, 300]))
+    p = int(rng.integers(4, 400))
+    max_k = int(rng.choice([0, 1, 3, 4, 5, 8, 21, 60]))
+    gt, plan, want = _case(rng, n, p, H, max_k)
+    dplan = engine.DevicePlan(plan)
+    gt_dev = torch.from_numpy(gt).cuda()
+    planes = engine.alloc_planes(n, plan.n_keys, gt_dev.device)
+    engine.pack(dplan, gt_dev.data_ptr(), gt_dev.stride(), n, planes)
+    pitch = engine.out_pitch(H) + 16 * int(rng.integers(0, 3))
+    for kernel in ("half", "tile"):
+        monkeypatch.setenv("HT_TRANSFORM_KERNEL", kernel)
+        out = torch.full((n, pitch), 5, dtype=torch.uint8, device="cuda")
+        engine.transform_u8(dplan, planes, n, out.data_ptr(), pitch, method="direct")
+        torch.cuda.synchronize()
+        got = out[:, : 2 * H].cpu().numpy().reshape(n, H, 2).view(np.bool_)
+        np.testing.assert_array_equal(got, want, err_msg=f"{kernel} n={n} H={H} p={p} max_k={max_k}")
+        assert bool((out[:, 2 * H :] == 5).all())
