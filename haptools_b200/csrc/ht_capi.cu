@@ -44,12 +44,16 @@ int bad_arg(const char* what) {
 namespace {
 constexpr int kMaxCopyThreads = 8, kBufsPerThread = 2;
 constexpr size_t kBounceBytes = 8u << 20;
+constexpr int kMaxBounceDevs = 16;
 struct Bounce {
     std::mutex mu;  // one staged upload at a time per process
     uint8_t* buf[kMaxCopyThreads][kBufsPerThread] = {};
-    cudaEvent_t ev[kMaxCopyThreads][kBufsPerThread] = {};
-    bool used[kMaxCopyThreads][kBufsPerThread] = {};
-    int dev = -1;
+    cudaEvent_t ev[kMaxBounceDevs][kMaxCopyThreads][kBufsPerThread] = {};  // an event belongs to a device
+    int last_dev[kMaxCopyThreads][kBufsPerThread];                          // device of the buffer's last DMA, -1: none
+    Bounce() {
+        for (auto& row : last_dev)
+            for (int& v : row) v = -1;
+    }
 };
 Bounce g_bounce;
 
@@ -71,7 +75,8 @@ void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, cons
     int b = 0;
     for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
         const int64_t rows = height - r0 < rows_per_block ? height - r0 : rows_per_block;
-        if (g_bounce.used[t][b]) e = cudaEventSynchronize(g_bounce.ev[t][b]);  // its last DMA has left
+        const int ld = g_bounce.last_dev[t][b];
+        if (ld >= 0) e = cudaEventSynchronize(g_bounce.ev[ld][t][b]);  // its last DMA (on any device) has left
         if (e != cudaSuccess) break;
         uint8_t* stage = g_bounce.buf[t][b];
         const uint8_t* s = src + r0 * src_pitch;
@@ -82,8 +87,8 @@ void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, cons
         }
         e = cudaMemcpy2DAsync(dst + r0 * dst_pitch, (size_t)dst_pitch, stage, (size_t)width, (size_t)width, (size_t)rows,
                               cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[t][b], st);
-        g_bounce.used[t][b] = e == cudaSuccess;
+        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[dev][t][b], st);
+        g_bounce.last_dev[t][b] = e == cudaSuccess ? dev : -1;
     }
     *err = e;
 }
@@ -101,27 +106,11 @@ static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int6
         for (int b = 0; b < kBufsPerThread; ++b) {
             if (!g_bounce.buf[t][b])
                 HT_CUDA_TRY(cudaHostAlloc((void**)&g_bounce.buf[t][b], kBounceBytes, cudaHostAllocPortable));
-            if (g_bounce.ev[t][b] && g_bounce.dev != dev) {  // events belong to a device: remake them after a switch
-                if (g_bounce.used[t][b]) cudaEventSynchronize(g_bounce.ev[t][b]);
-                cudaEventDestroy(g_bounce.ev[t][b]);
-                g_bounce.ev[t][b] = nullptr;
-                g_bounce.used[t][b] = false;
-            }
-            if (!g_bounce.ev[t][b]) HT_CUDA_TRY(cudaEventCreateWithFlags(&g_bounce.ev[t][b], cudaEventDisableTiming));
+            if (!g_bounce.ev[dev][t][b])
+                HT_CUDA_TRY(cudaEventCreateWithFlags(&g_bounce.ev[dev][t][b], cudaEventDisableTiming));
         }
     }
-    if (g_bounce.dev != dev) {  // buffers of threads not used this time: drop their stale events too
-        for (int t = nt; t < kMaxCopyThreads; ++t)
-            for (int b = 0; b < kBufsPerThread; ++b)
-                if (g_bounce.ev[t][b]) {
-                    if (g_bounce.used[t][b]) cudaEventSynchronize(g_bounce.ev[t][b]);
-                    cudaEventDestroy(g_bounce.ev[t][b]);
-                    g_bounce.ev[t][b] = nullptr;
-                    g_bounce.used[t][b] = false;
-                }
-    }
-    g_bounce.dev = dev;
-    cudaError_t errs[kMaxCopyThreads];
+    cudaError_t errs[kMaxCopyThreads] = {};  // cudaSuccess
     std::vector<std::thread> th;
     th.reserve(nt > 1 ? nt - 1 : 0);
     uint8_t* d = static_cast<uint8_t*>(dst);
@@ -167,7 +156,9 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
         case HT_COPY_D2D: k = cudaMemcpyDeviceToDevice; break;
         default: return ht::bad_arg("ht_copy2d: unknown kind");
     }
-    if (kind == HT_COPY_H2D && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes) {
+    int cur_dev = 0;
+    if (kind == HT_COPY_H2D && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes &&
+        cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev < ht::kMaxBounceDevs) {
         cudaPointerAttributes at;
         const cudaError_t e = cudaPointerGetAttributes(&at, src);
         if (e != cudaSuccess) cudaGetLastError();  // old drivers report unregistered memory as an error

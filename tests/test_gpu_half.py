@@ -148,6 +148,9 @@ def test_pageable_upload_through_bounce_buffers(layout):
     np.testing.assert_array_equal(got, want)
     got = engine.transform_host(arr, plan)
     np.testing.assert_array_equal(got, want)
+    # chunks dealt round-robin to every GPU of the box: the bounce buffers serve several devices in turn
+    got = engine.transform_host(arr, plan, chunk_samples=4096, devices="all")
+    np.testing.assert_array_equal(got, want)
 
 
 @pytest.mark.parametrize("seed", range(12))
