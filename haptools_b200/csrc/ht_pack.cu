@@ -743,12 +743,26 @@ __device__ __forceinline__ void insert_bytes(uint32_t (&dst)[4], uint32_t src, i
     for (int k = 0; k < 4; ++k) dst[k] = prmt(dst[k], src, keep | ((4u + k) << (4 * q)));
 }
 
+// kSlab: the mapping for LONG rows (pitch of a MB and more: every row of a tile lies in its own 2 MB
+// page, 1,024 pages per tile against a TLB reach of 128).  CTA = 4 words (128 rows) x 512 columns, the
+// grid is slab-major inside a tile, so all CTAs in flight read the same 128 rows (128 pages) and a CTA
+// reads 1 KB of every row; warp = 4 words x 64 columns (a load instruction reads 4 rows x 128 bytes), a
+// record is stored 4 words (one 32-byte sector) per instruction.  n_cblocks then counts (slab, 512-column
+// block) pairs: 8 * ceil(n_cols / 512).
+constexpr int kSm2SlabCols = 512, kSm2SlabsPerTile = 8;
+constexpr int64_t kSm2SlabMinPitch = 0;  // bytes between rows from which the slab mapping is used: always (it is
+                                         // faster at every pitch measured, 100 KB to 2 MB: profiles/exp_pack_pitch2.py)
+
+template <bool kSlab>
 __global__ void __launch_bounds__(kPackThreads, 3)
 pack_sm2_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_cblocks;
-    const int word = (warp >> 2) * 16 + (lane >> 1);
-    const int64_t col0 = (cblock0 + blockIdx.x % n_cblocks) * kSm2CtaCols + (warp & 3) * 16 + (lane & 1) * 8;
+    const uint32_t xb = blockIdx.x % n_cblocks;
+    const uint32_t n_cb = kSlab ? n_cblocks / kSm2SlabsPerTile : n_cblocks;
+    const int word = kSlab ? (int)(xb / n_cb) * 4 + (lane >> 3) : (warp >> 2) * 16 + (lane >> 1);
+    const int64_t col0 = kSlab ? (cblock0 + xb % n_cb) * kSm2SlabCols + warp * 64 + (lane & 7) * 8
+                               : (cblock0 + xb) * kSm2CtaCols + (warp & 3) * 16 + (lane & 1) * 8;
     const int ncols = (int)min((int64_t)8, a.n_cols - col0);  // may be <= 0
     if (ncols <= 0) return;
     const int64_t s0 = tile * kTileSamples + 32 * word;
@@ -1424,11 +1438,16 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                 return HT_ERR_UNSUPPORTED;
             }
             const int64_t n_cblocks = (n_cols + kSm2CtaCols - 1) / kSm2CtaCols;
+            // long rows (see pack_sm2_kernel<true>); HT_PACK_SM2_KERNEL=slab|tile overrides (measurements, tests)
+            const char* sm2_form = getenv("HT_PACK_SM2_KERNEL");
+            const bool sm2_slab = sm2_form ? sm2_form[0] == 's' : gt_s_samp >= kSm2SlabMinPitch;
+            const int64_t n_slab_blocks = kSm2SlabsPerTile * ((n_cols + kSm2SlabCols - 1) / kSm2SlabCols);
             const char* anc_form = getenv("HT_PACK_ANC_KERNEL");  // "warp" = pack_sm2_anc_kernel (A/B measurements, tests)
             const bool anc_line = !(anc_form && anc_form[0] == 'w');
             if (int rc = anc ? (anc_line ? launch_tiled(pack_sm2_anc_line_kernel, a, n_cblocks, 0, true, st, kSm2AncLineSmem)
                                          : launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem))
-                             : launch_tiled(pack_sm2_kernel, a, n_cblocks, 0, true, st))
+                             : (sm2_slab ? launch_tiled(pack_sm2_kernel<true>, a, n_slab_blocks, 0, true, st)
+                                         : launch_tiled(pack_sm2_kernel<false>, a, n_cblocks, 0, true, st)))
                 return rc;
             if (t->n_var_other > 0) {  // the few variants with other keys: generic kernel
                 PackArgs o = a;
