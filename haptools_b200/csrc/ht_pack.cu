@@ -1108,27 +1108,36 @@ pack_sm2_anc_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64
 // (93 registers).  Default form for ancestry plans: 18.0 ms against 19.7 ms on the ancestry config
 // (0.74 of the measured HBM peak); 3 CTAs per SM (80 registers) are SLOWER (22.9 ms), see DESIGN.md.
 // -----------------------------------------------------------------------------------------
-constexpr int kAncLineKeyStage = 1024;  // staged (allele, label) pairs per CTA (its 64 columns)
-constexpr size_t kSm2AncLineSmem = sizeof(uint32_t) * 64 * kPackThreads + sizeof(int2) * kSm2CtaCols +
-                                   sizeof(uint16_t) * kAncLineKeyStage + sizeof(int) * 2;
+constexpr int kAncLineKeyStage = 2048;  // staged (allele, label) pairs per CTA (its 64 or 512 columns)
+constexpr size_t sm2_anc_line_smem(bool slab) {
+    return sizeof(uint32_t) * 64 * kPackThreads + sizeof(int2) * (slab ? kSm2SlabCols : kSm2CtaCols) +
+           sizeof(uint16_t) * kAncLineKeyStage + sizeof(int) * 2;
+}
 
 #ifndef HT_ANC_LINE_MIN_CTAS
 #define HT_ANC_LINE_MIN_CTAS 2
 #endif
+// kSlab: CTA = 4 words x 512 columns, slab-major grid, as in pack_sm2_kernel<true> (n_cblocks counts
+// (slab, 512-column block) pairs); else CTA = 32 words x 64 columns.
+template <bool kSlab>
 __global__ void __launch_bounds__(kPackThreads, HT_ANC_LINE_MIN_CTAS)
 pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
+    constexpr int kCols = kSlab ? kSm2SlabCols : kSm2CtaCols;  // columns of the CTA
     extern __shared__ uint32_t s_dyn[];
     uint32_t* gl = s_dyn + threadIdx.x;  // [(q * 4 + plane) * 4 + j][thread]; plane 0 = allele 1, 1..3 = label bits
-    int2* s_kr = reinterpret_cast<int2*>(s_dyn + 64 * kPackThreads);  // key range of each of the CTA's 64 columns
-    uint16_t* s_ki = reinterpret_cast<uint16_t*>(s_kr + kSm2CtaCols);
+    int2* s_kr = reinterpret_cast<int2*>(s_dyn + 64 * kPackThreads);  // key range of each of the CTA's columns
+    uint16_t* s_ki = reinterpret_cast<uint16_t*>(s_kr + kCols);
     int* s_span = reinterpret_cast<int*>(s_ki + kAncLineKeyStage);     // {first key, end key} of the CTA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_cblocks;
-    const int word = warp * 4 + (lane >> 3);
-    const int64_t wcol0 = (cblock0 + blockIdx.x % n_cblocks) * kSm2CtaCols;  // the CTA's first column
+    const uint32_t xb = blockIdx.x % n_cblocks;
+    const uint32_t n_cb = kSlab ? n_cblocks / kSm2SlabsPerTile : n_cblocks;
+    const int word = kSlab ? (int)(xb / n_cb) * 4 + (lane >> 3) : warp * 4 + (lane >> 3);
+    const int64_t wcol0 = (cblock0 + xb % n_cb) * kCols;  // the CTA's first column
     if (wcol0 >= a.n_cols) return;  // CTA-uniform
-    const int64_t col0 = wcol0 + (lane & 7) * 8;
+    const int ccol = (kSlab ? warp * 64 : 0) + (lane & 7) * 8;  // my first column inside the CTA
+    const int64_t col0 = wcol0 + ccol;
     const int ncols = (int)max((int64_t)0, min((int64_t)8, a.n_cols - col0));
     const int64_t s0 = tile * kTileSamples + 32 * word;
     const int nrows = (int)max((int64_t)0, min((int64_t)32, a.n - s0));
@@ -1137,10 +1146,15 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
     int2* my_kr = s_kr;
     uint16_t* my_ki = s_ki;
 
-    // (1) key ranges of the CTA's 64 columns (threads 0..63 fetch one each)
-    int2 kr = make_int2(0, 0);
-    if (threadIdx.x < kSm2CtaCols && wcol0 + threadIdx.x < a.n_cols)
-        kr = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + threadIdx.x);
+    // (1) key ranges of the CTA's columns (one or two per thread)
+    constexpr int kKrPerThread = (kCols + kPackThreads - 1) / kPackThreads;
+    int2 kr[kKrPerThread];
+#pragma unroll
+    for (int i = 0; i < kKrPerThread; ++i) {
+        const int c = threadIdx.x + i * kPackThreads;
+        kr[i] = make_int2(0, 0);
+        if (c < kCols && wcol0 + c < a.n_cols) kr[i] = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + c);
+    }
     if (threadIdx.x == 0) {
         s_span[0] = 0x7fffffff;
         s_span[1] = 0;
@@ -1185,11 +1199,15 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
     }
 
     // (3) publish the key ranges, find the CTA's key span, fetch its (allele, label) bytes
-    if (threadIdx.x < kSm2CtaCols) {
-        s_kr[threadIdx.x] = kr;
-        if (kr.y > 0) {
-            atomicMin(&s_span[0], kr.x);
-            atomicMax(&s_span[1], kr.x + kr.y);
+#pragma unroll
+    for (int i = 0; i < kKrPerThread; ++i) {
+        const int c = threadIdx.x + i * kPackThreads;
+        if (c < kCols) {
+            s_kr[c] = kr[i];
+            if (kr[i].y > 0) {
+                atomicMin(&s_span[0], kr[i].x);
+                atomicMax(&s_span[1], kr[i].x + kr[i].y);
+            }
         }
     }
     __syncthreads();
@@ -1274,7 +1292,7 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
         if (d) {
             // invalid plane (GT byte >= 2 or label byte >= 8), only for lanes that saw such a byte: a
             // second read of my rows' word j (L1/L2 hits), one row at a time
-            const int c_lo = (lane & 7) * 8 + 2 * j;
+            const int c_lo = ccol + 2 * j;
             const uint32_t refmask = (my_kr[c_lo].y > 0 ? 0x0000ffffu : 0u) | (my_kr[c_lo + 1].y > 0 ? 0xffff0000u : 0u);
             const int nc = ncols - 2 * j;  // columns of this word that exist (may be <= 0)
             const uint8_t* pg = gbase + 4 * j;
@@ -1297,7 +1315,7 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
         }
 #pragma unroll
         for (int cp = 0; cp < 2; ++cp) {
-            const int2 r = my_kr[(lane & 7) * 8 + 2 * j + cp];
+            const int2 r = my_kr[ccol + 2 * j + cp];
 #pragma unroll 1
             for (int t = 0; t < r.y; ++t) {
                 const int key = r.x + t;
@@ -1444,7 +1462,12 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
             const int64_t n_slab_blocks = kSm2SlabsPerTile * ((n_cols + kSm2SlabCols - 1) / kSm2SlabCols);
             const char* anc_form = getenv("HT_PACK_ANC_KERNEL");  // "warp" = pack_sm2_anc_kernel (A/B measurements, tests)
             const bool anc_line = !(anc_form && anc_form[0] == 'w');
-            if (int rc = anc ? (anc_line ? launch_tiled(pack_sm2_anc_line_kernel, a, n_cblocks, 0, true, st, kSm2AncLineSmem)
+            // the ancestry kernel keeps the tile mapping: its line-consuming loads make it insensitive to the row
+            // pitch (4.7 TB/s from 100 KB to 2 MB) and the slab mapping repeats its key staging 8 x per tile
+            // (18.2 vs 21.2 ms on the ancestry config, profiles/exp_pack_pitch3.py); slab only on request
+            const bool anc_slab = sm2_form && sm2_form[0] == 's';
+            if (int rc = anc ? (anc_line ? (anc_slab ? launch_tiled(pack_sm2_anc_line_kernel<true>, a, n_slab_blocks, 0, true, st, sm2_anc_line_smem(true))
+                                                     : launch_tiled(pack_sm2_anc_line_kernel<false>, a, n_cblocks, 0, true, st, sm2_anc_line_smem(false)))
                                          : launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem))
                              : (sm2_slab ? launch_tiled(pack_sm2_kernel<true>, a, n_slab_blocks, 0, true, st)
                                          : launch_tiled(pack_sm2_kernel<false>, a, n_cblocks, 0, true, st)))

@@ -176,3 +176,40 @@ def test_random_shapes_both_forms(monkeypatch, seed):
         got = out[:, : 2 * H].cpu().numpy().reshape(n, H, 2).view(np.bool_)
         np.testing.assert_array_equal(got, want, err_msg=f"{kernel} n={n} H={H} p={p} max_k={max_k}")
         assert bool((out[:, 2 * H :] == 5).all())
+
+
+@pytest.mark.parametrize("mapping", ["slab", "tile"])
+@pytest.mark.parametrize("kind", ["plain", "ancestry"])
+@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (129, 520, 40), (1032, 40, 70), (2504, 600, 200), (3104, 1032, 333)])
+def test_sample_major_pack_mappings_vs_oracle(monkeypatch, mapping, kind, n, p, H):
+    """The two CTA mappings of the sample-major biallelic pack kernels (csrc/ht_pack.cu: slab = 128 rows x
+    512 columns, the default of the plain kernel; tile = 1,024 rows x 64 columns, the default with ancestry)
+    against the oracle: ragged rows and columns, missing calls, column counts around 512."""
+    monkeypatch.setenv("HT_PACK_SM2_KERNEL", mapping)
+    from haptools_b200 import _cuda
+
+    rng = np.random.default_rng(31 * n + p + H)
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.01] = 255
+    anc = None
+    k = rng.integers(0, min(6, p) + 1, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, dtype=np.int64)])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    hap_label = ref_label = None
+    if kind == "ancestry":
+        anc = np.ascontiguousarray(np.repeat(rng.integers(0, 5, size=(n, (p + 6) // 7, 2), dtype=np.uint8), 7, axis=1)[:, :p])
+        hap_label = rng.integers(0, 5, size=H)
+        ref_label = np.repeat(hap_label, k)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, ref_label)
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    cols = ref_col.astype(np.int64)
+    want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs,
+                              anc[:, cols] if anc is not None else None,
+                              hap_label.astype(np.uint8) if hap_label is not None else None)
+    dplan = engine.DevicePlan(plan)
+    out = engine.transform_device(torch.from_numpy(gt).cuda(), dplan,
+                                  ancestry=torch.from_numpy(anc).cuda() if anc is not None else None,
+                                  pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC if p % 8 == 0 else _cuda.HT_PACK_AUTO)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=f"{mapping}/{kind}")
