@@ -1117,8 +1117,8 @@ constexpr size_t sm2_anc_line_smem(bool slab) {
 #ifndef HT_ANC_LINE_MIN_CTAS
 #define HT_ANC_LINE_MIN_CTAS 2
 #endif
-// kSlab: CTA = 4 words x 512 columns, slab-major grid, as in pack_sm2_kernel<true> (n_cblocks counts
-// (slab, 512-column block) pairs); else CTA = 32 words x 64 columns.
+// kSlab: CTA = 512 columns, walking the 8 slabs (4 words = 128 rows each) of its tile one after the other
+// with the key tables staged once (n_cblocks counts 512-column blocks); else CTA = 32 words x 64 columns.
 template <bool kSlab>
 __global__ void __launch_bounds__(kPackThreads, HT_ANC_LINE_MIN_CTAS)
 pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, int64_t tile0) {
@@ -1131,83 +1131,25 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_cblocks;
-    const uint32_t xb = blockIdx.x % n_cblocks;
-    const uint32_t n_cb = kSlab ? n_cblocks / kSm2SlabsPerTile : n_cblocks;
-    const int word = kSlab ? (int)(xb / n_cb) * 4 + (lane >> 3) : warp * 4 + (lane >> 3);
-    const int64_t wcol0 = (cblock0 + xb % n_cb) * kCols;  // the CTA's first column
+    const int64_t wcol0 = (cblock0 + blockIdx.x % n_cblocks) * kCols;  // the CTA's first column
     if (wcol0 >= a.n_cols) return;  // CTA-uniform
     const int ccol = (kSlab ? warp * 64 : 0) + (lane & 7) * 8;  // my first column inside the CTA
     const int64_t col0 = wcol0 + ccol;
     const int ncols = (int)max((int64_t)0, min((int64_t)8, a.n_cols - col0));
-    const int64_t s0 = tile * kTileSamples + 32 * word;
-    const int nrows = (int)max((int64_t)0, min((int64_t)32, a.n - s0));
-    const bool have_rows = ncols > 0 && nrows > 0;
-    const bool full = nrows == 32 && ncols == 8;
-    int2* my_kr = s_kr;
-    uint16_t* my_ki = s_ki;
 
-    // (1) key ranges of the CTA's columns (one or two per thread)
-    constexpr int kKrPerThread = (kCols + kPackThreads - 1) / kPackThreads;
-    int2 kr[kKrPerThread];
-#pragma unroll
-    for (int i = 0; i < kKrPerThread; ++i) {
-        const int c = threadIdx.x + i * kPackThreads;
-        kr[i] = make_int2(0, 0);
-        if (c < kCols && wcol0 + c < a.n_cols) kr[i] = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + c);
-    }
+    // (1) key ranges of the CTA's columns, its key span, the (allele, label) bytes of those keys
     if (threadIdx.x == 0) {
         s_span[0] = 0x7fffffff;
         s_span[1] = 0;
     }
     __syncthreads();
-
-    // (2) genotype rows -> 8-row block accumulators of the allele-1 plane, parked in thread-private shared
-    //     memory like those of the label bits below: registers are the load buffers, nothing else stays live
-    uint32_t d = 0u;
-    const uint8_t* gbase = a.gt + s0 * a.gs + col0 * 2;
-    const uint8_t* lbase = a.anc + s0 * a.as + col0 * 2;
-    if (have_rows) {
-        const uint8_t* p = gbase;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            uint4 x[8];
-            if (full) {
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint4*>(p));
-            } else {
-#pragma unroll
-                for (int rr = 0; rr < 8; ++rr, p += a.gs) {
-                    x[rr] = make_uint4(0u, 0u, 0u, 0u);
-                    if (8 * q + rr < nrows) x[rr] = load_row16(p, ncols);
-                }
-            }
-            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
-#pragma unroll
-            for (int rr = 7; rr >= 0; --rr) {
-                a0 = (a0 << 1) + (x[rr].x & 0x01010101u);
-                a1 = (a1 << 1) + (x[rr].y & 0x01010101u);
-                a2 = (a2 << 1) + (x[rr].z & 0x01010101u);
-                a3 = (a3 << 1) + (x[rr].w & 0x01010101u);
-                d |= ((x[rr].x | x[rr].y) | (x[rr].z | x[rr].w)) & 0xfefefefeu;
-            }
-            uint32_t* dst = gl + (q * 16) * kPackThreads;
-            dst[0] = a0;
-            dst[kPackThreads] = a1;
-            dst[2 * kPackThreads] = a2;
-            dst[3 * kPackThreads] = a3;
-        }
-    }
-
-    // (3) publish the key ranges, find the CTA's key span, fetch its (allele, label) bytes
-#pragma unroll
-    for (int i = 0; i < kKrPerThread; ++i) {
-        const int c = threadIdx.x + i * kPackThreads;
-        if (c < kCols) {
-            s_kr[c] = kr[i];
-            if (kr[i].y > 0) {
-                atomicMin(&s_span[0], kr[i].x);
-                atomicMax(&s_span[1], kr[i].x + kr[i].y);
-            }
+    for (int c = threadIdx.x; c < kCols; c += kPackThreads) {
+        int2 kr = make_int2(0, 0);
+        if (wcol0 + c < a.n_cols) kr = __ldg(reinterpret_cast<const int2*>(a.col_key_range) + wcol0 + c);
+        s_kr[c] = kr;
+        if (kr.y > 0) {
+            atomicMin(&s_span[0], kr.x);
+            atomicMax(&s_span[1], kr.x + kr.y);
         }
     }
     __syncthreads();
@@ -1215,120 +1157,151 @@ pack_sm2_anc_line_kernel(const PackArgs a, uint32_t n_cblocks, int64_t cblock0, 
     if (kmax <= kmin) return;  // none of the CTA's columns is referenced (CTA-uniform)
     const int n_k = kmax - kmin;
     const bool ki_staged = n_k <= kAncLineKeyStage;
-    uint32_t ki_reg[kAncLineKeyStage / kPackThreads];
-#pragma unroll
-    for (int t = 0; t < kAncLineKeyStage / kPackThreads; ++t) {
-        const int idx = threadIdx.x + kPackThreads * t;
-        ki_reg[t] = 0u;
-        if (ki_staged && idx < n_k)
-            ki_reg[t] = (uint32_t)__ldg(a.key_allele + kmin + idx) | ((uint32_t)__ldg(a.key_label + kmin + idx) << 8);
+    if (ki_staged) {
+        for (int idx = threadIdx.x; idx < n_k; idx += kPackThreads)
+            s_ki[idx] = (uint16_t)((uint32_t)__ldg(a.key_allele + kmin + idx) | ((uint32_t)__ldg(a.key_label + kmin + idx) << 8));
     }
+    __syncthreads();
+    if (ncols <= 0) return;  // no barrier below
 
-    // (4) ancestry rows -> block accumulators of label bits 0..2, parked in shared memory
-    if (have_rows) {
-        const uint8_t* p = lbase;
+    uint32_t fl = 0u;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            uint4 c[8];
-            if (full) {
+    for (int part = 0; part < (kSlab ? kSm2SlabsPerTile : 1); ++part) {
+        const int word = kSlab ? part * 4 + (lane >> 3) : warp * 4 + (lane >> 3);
+        const int64_t s0 = tile * kTileSamples + 32 * word;
+        const int nrows = (int)max((int64_t)0, min((int64_t)32, a.n - s0));
+        const bool full = nrows == 32 && ncols == 8;
+        const uint8_t* gbase = a.gt + s0 * a.gs + col0 * 2;
+        const uint8_t* lbase = a.anc + s0 * a.as + col0 * 2;
+        uint32_t d = 0u;
+
+        // (2) genotype rows -> 8-row block accumulators of the allele-1 plane, parked in thread-private
+        //     shared memory like those of the label bits below: registers are the load buffers
+        if (nrows > 0) {
+            const uint8_t* p = gbase;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                uint4 x[8];
+                if (full) {
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr, p += a.as) c[rr] = __ldg(reinterpret_cast<const uint4*>(p));
-            } else {
+                    for (int rr = 0; rr < 8; ++rr, p += a.gs) x[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+                } else {
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr, p += a.as) {
-                    c[rr] = make_uint4(0u, 0u, 0u, 0u);
-                    if (8 * q + rr < nrows) c[rr] = load_row16(p, ncols);
+                    for (int rr = 0; rr < 8; ++rr, p += a.gs) {
+                        x[rr] = make_uint4(0u, 0u, 0u, 0u);
+                        if (8 * q + rr < nrows) x[rr] = load_row16(p, ncols);
+                    }
                 }
-            }
-#pragma unroll
-            for (int bit = 0; bit < 3; ++bit) {
                 uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
 #pragma unroll
-                for (int rr = 7; rr >= 0; --rr) {
-                    a0 = (a0 << 1) + ((c[rr].x >> bit) & 0x01010101u);
-                    a1 = (a1 << 1) + ((c[rr].y >> bit) & 0x01010101u);
-                    a2 = (a2 << 1) + ((c[rr].z >> bit) & 0x01010101u);
-                    a3 = (a3 << 1) + ((c[rr].w >> bit) & 0x01010101u);
+                for (int rr = 7; rr >= 0; --rr) {  // row rr ends at bit rr of its byte
+                    a0 = (a0 << 1) + (x[rr].x & 0x01010101u);
+                    a1 = (a1 << 1) + (x[rr].y & 0x01010101u);
+                    a2 = (a2 << 1) + (x[rr].z & 0x01010101u);
+                    a3 = (a3 << 1) + (x[rr].w & 0x01010101u);
+                    d |= ((x[rr].x | x[rr].y) | (x[rr].z | x[rr].w)) & 0xfefefefeu;
                 }
-                uint32_t* dst = gl + ((q * 4 + bit + 1) * 4) * kPackThreads;
+                uint32_t* dst = gl + (q * 16) * kPackThreads;
                 dst[0] = a0;
                 dst[kPackThreads] = a1;
                 dst[2 * kPackThreads] = a2;
                 dst[3 * kPackThreads] = a3;
             }
-#pragma unroll
-            for (int rr = 0; rr < 8; ++rr) d |= ((c[rr].x | c[rr].y) | (c[rr].z | c[rr].w)) & 0xf8f8f8f8u;
-        }
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < 64; ++i) gl[i * kPackThreads] = 0u;
-    }
-
-    // (5) publish the key bytes
-    if (ki_staged) {
-#pragma unroll
-        for (int t = 0; t < kAncLineKeyStage / kPackThreads; ++t)
-            if (threadIdx.x + kPackThreads * t < n_k) my_ki[threadIdx.x + kPackThreads * t] = (uint16_t)ki_reg[t];
-    }
-    __syncthreads();
-
-    // (6) every key of my 8 columns, one pair of columns (= one 4-byte word of my rows) at a time:
-    //     combine the planes, store word `word` of both strands.  The loop is rolled and nothing but the
-    //     shared-memory accumulators is carried into it.
-    if (ncols <= 0) return;
-    const uint32_t vm = valid_mask(a.n, tile, word);
-    uint32_t fl = 0u;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        uint32_t Wj[4], L[3][4], Zj[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int plane = 0; plane < 4; ++plane) {
-            uint32_t G[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) G[q] = gl[((q * 4 + plane) * 4 + j) * kPackThreads];
-            if (plane == 0) byte_transpose4(G, Wj);
-            else byte_transpose4(G, L[plane - 1]);
-        }
-        if (d) {
-            // invalid plane (GT byte >= 2 or label byte >= 8), only for lanes that saw such a byte: a
-            // second read of my rows' word j (L1/L2 hits), one row at a time
-            const int c_lo = ccol + 2 * j;
-            const uint32_t refmask = (my_kr[c_lo].y > 0 ? 0x0000ffffu : 0u) | (my_kr[c_lo + 1].y > 0 ? 0xffff0000u : 0u);
-            const int nc = ncols - 2 * j;  // columns of this word that exist (may be <= 0)
-            const uint8_t* pg = gbase + 4 * j;
-            const uint8_t* pl = lbase + 4 * j;
+            // (3) ancestry rows -> block accumulators of label bits 0..2
+            p = lbase;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
-                uint32_t z = 0u;
-#pragma unroll 1
-                for (int rr = 0; rr < 8; ++rr, pg += a.gs, pl += a.as) {  // row rr enters at bit 7, ends at bit rr
-                    uint32_t x = 0u, c = 0u;
-                    if (8 * q + rr < nrows && nc > 0) {
-                        x = load_cols4(pg, nc);
-                        c = load_cols4(pl, nc);
-                    }
-                    z = (z >> 1) | nz_bytes_msb((x & 0xfefefefeu) | (c & 0xf8f8f8f8u));
-                    if (a.flags) fl |= qc_flags4(x & refmask);
-                }
-                insert_bytes(Zj, z, q);
-            }
-        }
+                uint4 c[8];
+                if (full) {
 #pragma unroll
-        for (int cp = 0; cp < 2; ++cp) {
-            const int2 r = my_kr[ccol + 2 * j + cp];
+                    for (int rr = 0; rr < 8; ++rr, p += a.as) c[rr] = __ldg(reinterpret_cast<const uint4*>(p));
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr, p += a.as) {
+                        c[rr] = make_uint4(0u, 0u, 0u, 0u);
+                        if (8 * q + rr < nrows) c[rr] = load_row16(p, ncols);
+                    }
+                }
+#pragma unroll
+                for (int bit = 0; bit < 3; ++bit) {
+                    uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+                    for (int rr = 7; rr >= 0; --rr) {
+                        a0 = (a0 << 1) + ((c[rr].x >> bit) & 0x01010101u);
+                        a1 = (a1 << 1) + ((c[rr].y >> bit) & 0x01010101u);
+                        a2 = (a2 << 1) + ((c[rr].z >> bit) & 0x01010101u);
+                        a3 = (a3 << 1) + ((c[rr].w >> bit) & 0x01010101u);
+                    }
+                    uint32_t* dst = gl + ((q * 4 + bit + 1) * 4) * kPackThreads;
+                    dst[0] = a0;
+                    dst[kPackThreads] = a1;
+                    dst[2 * kPackThreads] = a2;
+                    dst[3 * kPackThreads] = a3;
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) d |= ((c[rr].x | c[rr].y) | (c[rr].z | c[rr].w)) & 0xf8f8f8f8u;
+            }
+        } else {
 #pragma unroll 1
-            for (int t = 0; t < r.y; ++t) {
-                const int key = r.x + t;
-                const uint32_t info = ki_staged ? (uint32_t)my_ki[key - kmin]
-                                                : ((uint32_t)__ldg(a.key_allele + key) | ((uint32_t)__ldg(a.key_label + key) << 8));
-                const uint32_t mA = (info & 1u) ? 0u : 0xffffffffu, m0 = (info & 0x100u) ? 0u : 0xffffffffu;
-                const uint32_t m1 = (info & 0x200u) ? 0u : 0xffffffffu, m2 = (info & 0x400u) ? 0u : 0xffffffffu;
-                uint2 o;
-                o.x = (Wj[2 * cp] ^ mA) & (L[0][2 * cp] ^ m0) & (L[1][2 * cp] ^ m1) & (L[2][2 * cp] ^ m2) &
-                      ~Zj[2 * cp] & vm;
-                o.y = (Wj[2 * cp + 1] ^ mA) & (L[0][2 * cp + 1] ^ m0) & (L[1][2 * cp + 1] ^ m1) &
-                      (L[2][2 * cp + 1] ^ m2) & ~Zj[2 * cp + 1] & vm;
-                record(a, tile, (uint32_t)key)[word] = o;
+            for (int i = 0; i < 64; ++i) gl[i * kPackThreads] = 0u;
+        }
+
+        // (4) every key of my 8 columns, one pair of columns (= one 4-byte word of my rows) at a time:
+        //     combine the planes, store word `word` of both strands.  The loop is rolled and nothing but the
+        //     shared-memory accumulators is carried into it.
+        const uint32_t vm = valid_mask(a.n, tile, word);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t Wj[4], L[3][4], Zj[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int plane = 0; plane < 4; ++plane) {
+                uint32_t G[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) G[q] = gl[((q * 4 + plane) * 4 + j) * kPackThreads];
+                if (plane == 0) byte_transpose4(G, Wj);
+                else byte_transpose4(G, L[plane - 1]);
+            }
+            if (d) {
+                // invalid plane (GT byte >= 2 or label byte >= 8), only for lanes that saw such a byte: a
+                // second read of my rows' word j (L1/L2 hits), one row at a time
+                const int c_lo = ccol + 2 * j;
+                const uint32_t refmask = (s_kr[c_lo].y > 0 ? 0x0000ffffu : 0u) | (s_kr[c_lo + 1].y > 0 ? 0xffff0000u : 0u);
+                const int nc = ncols - 2 * j;  // columns of this word that exist (may be <= 0)
+                const uint8_t* pg = gbase + 4 * j;
+                const uint8_t* pl = lbase + 4 * j;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t z = 0u;
+#pragma unroll 1
+                    for (int rr = 0; rr < 8; ++rr, pg += a.gs, pl += a.as) {  // row rr enters at bit 7, ends at bit rr
+                        uint32_t x = 0u, c = 0u;
+                        if (8 * q + rr < nrows && nc > 0) {
+                            x = load_cols4(pg, nc);
+                            c = load_cols4(pl, nc);
+                        }
+                        z = (z >> 1) | nz_bytes_msb((x & 0xfefefefeu) | (c & 0xf8f8f8f8u));
+                        if (a.flags) fl |= qc_flags4(x & refmask);
+                    }
+                    insert_bytes(Zj, z, q);
+                }
+            }
+#pragma unroll
+            for (int cp = 0; cp < 2; ++cp) {
+                const int2 r = s_kr[ccol + 2 * j + cp];
+#pragma unroll 1
+                for (int t = 0; t < r.y; ++t) {
+                    const int key = r.x + t;
+                    const uint32_t info = ki_staged ? (uint32_t)s_ki[key - kmin]
+                                                    : ((uint32_t)__ldg(a.key_allele + key) | ((uint32_t)__ldg(a.key_label + key) << 8));
+                    const uint32_t mA = (info & 1u) ? 0u : 0xffffffffu, m0 = (info & 0x100u) ? 0u : 0xffffffffu;
+                    const uint32_t m1 = (info & 0x200u) ? 0u : 0xffffffffu, m2 = (info & 0x400u) ? 0u : 0xffffffffu;
+                    uint2 o;
+                    o.x = (Wj[2 * cp] ^ mA) & (L[0][2 * cp] ^ m0) & (L[1][2 * cp] ^ m1) & (L[2][2 * cp] ^ m2) &
+                          ~Zj[2 * cp] & vm;
+                    o.y = (Wj[2 * cp + 1] ^ mA) & (L[0][2 * cp + 1] ^ m0) & (L[1][2 * cp + 1] ^ m1) &
+                          (L[2][2 * cp + 1] ^ m2) & ~Zj[2 * cp + 1] & vm;
+                    record(a, tile, (uint32_t)key)[word] = o;
+                }
             }
         }
     }
@@ -1466,7 +1439,7 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
             // pitch (4.7 TB/s from 100 KB to 2 MB) and the slab mapping repeats its key staging 8 x per tile
             // (18.2 vs 21.2 ms on the ancestry config, profiles/exp_pack_pitch3.py); slab only on request
             const bool anc_slab = sm2_form && sm2_form[0] == 's';
-            if (int rc = anc ? (anc_line ? (anc_slab ? launch_tiled(pack_sm2_anc_line_kernel<true>, a, n_slab_blocks, 0, true, st, sm2_anc_line_smem(true))
+            if (int rc = anc ? (anc_line ? (anc_slab ? launch_tiled(pack_sm2_anc_line_kernel<true>, a, n_slab_blocks / kSm2SlabsPerTile, 0, true, st, sm2_anc_line_smem(true))
                                                      : launch_tiled(pack_sm2_anc_line_kernel<false>, a, n_cblocks, 0, true, st, sm2_anc_line_smem(false)))
                                          : launch_tiled(pack_sm2_anc_kernel, a, n_cblocks, 0, true, st, kSm2AncSmem))
                              : (sm2_slab ? launch_tiled(pack_sm2_kernel<true>, a, n_slab_blocks, 0, true, st)
