@@ -75,7 +75,10 @@ extern "C" {
                                    builds the planes of every allele-0/1 key with 128-byte
                                    coalesced record stores; variants listed in
                                    tables->var_other go through the generic kernel.  What
-                                   HT_PACK_AUTO picks when it can.  With ancestry the
+                                   HT_PACK_AUTO picks when it can.  The plain kernel runs with
+                                   the slab mapping (CTA = 128 rows x 512 columns, 32-byte
+                                   record stores; HT_PACK_SM2_KERNEL=tile: 1,024 rows x 64
+                                   columns, 128-byte record stores).  With ancestry the
                                    line-consuming form runs (a warp reads 4 rows x 128 bytes,
                                    32-byte record stores); HT_PACK_ANC_KERNEL=warp in the
                                    environment selects the earlier form (measurements, tests) */
