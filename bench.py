@@ -394,11 +394,17 @@ def run_b200(args):
         ne = min(args.e2e_samples, n)
         del out, planes, workspace
         torch.cuda.empty_cache()
-        host_gt = engine.pinned_empty((ne, p, 2))
+        def host_array():
+            # the workload's memory layout: variant-major = the VCF reader's (p, n, 2) array seen as (n, p, 2)
+            if w["layout"] == "variant_major":
+                return engine.pinned_empty((p, ne, 2)).transpose(1, 0, 2)
+            return engine.pinned_empty((ne, p, 2))
+
+        host_gt = host_array()
         host_gt[:] = synth.synth_gt(min(ne, 256), p, w["seed"] + 1, mode=1, sample_offset=sample_offset)[np.arange(ne) % min(ne, 256)]
         host_anc = None
         if w["n_pops"]:
-            host_anc = engine.pinned_empty((ne, p, 2))
+            host_anc = host_array()
             host_anc[:] = synth.synth_ancestry(min(ne, 256), p, w["seed"] + 2, w["n_pops"], 2000, sample_offset=sample_offset)[np.arange(ne) % min(ne, 256)]
         host_out = engine.pinned_empty((ne, H, 2))
         for _ in range(2):
@@ -417,7 +423,7 @@ def run_b200(args):
             dt = float(t.item())
         e2e = {
             "value": world * ne * H * 2 / dt, "unit": UNIT,
-            "h2d_bytes_per_step": int(host_gt.nbytes * (2 if host_anc is not None else 1)) * world,
+            "h2d_bytes_per_step": engine.upload_bytes(host_gt, plan, host_anc) * world,
             "d2h_bytes_per_step": int(res.nbytes) * world,
             "samples_per_gpu": ne, "ms": dt * 1e3, "cpu_binding_rank0": numa,
             "api": "haptools_b200.engine.transform_host (the call Haplotypes.transform makes) on pinned host arrays; "

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ht_relayout_u8": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p]),
     "ht_bp_ancestry": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "ht_copy2d": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i32, _p]),
+    "ht_copy_rows_h2d": (_i32, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "ht_host_register": (_i32, [_p, _sz]),
     "ht_host_unregister": (_i32, [_p]),
 }

@@ -69,8 +69,10 @@ int host_threads() {
 }
 
 // worker t of nt: row blocks t, t + nt, ... through its own pair of bounce buffers
+// `row_idx` (optional): output row r is source row row_idx[r] (a gather of selected rows)
 void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, const uint8_t* src, int64_t src_pitch,
-                   int64_t width, int64_t height, int64_t rows_per_block, cudaStream_t st, cudaError_t* err) {
+                   int64_t width, int64_t height, int64_t rows_per_block, const uint32_t* row_idx, cudaStream_t st,
+                   cudaError_t* err) {
     cudaError_t e = t ? cudaSetDevice(dev) : cudaSuccess;  // a new host thread starts on device 0
     int b = 0;
     for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
@@ -80,7 +82,9 @@ void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, cons
         if (e != cudaSuccess) break;
         uint8_t* stage = g_bounce.buf[t][b];
         const uint8_t* s = src + r0 * src_pitch;
-        if (src_pitch == width) {
+        if (row_idx) {
+            for (int64_t r = 0; r < rows; ++r) memcpy(stage + r * width, src + (int64_t)row_idx[r0 + r] * src_pitch, (size_t)width);
+        } else if (src_pitch == width) {
             memcpy(stage, s, (size_t)(rows * width));
         } else {
             for (int64_t r = 0; r < rows; ++r) memcpy(stage + r * width, s + r * src_pitch, (size_t)width);
@@ -95,7 +99,7 @@ void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, cons
 }  // namespace
 
 static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
-                             int64_t height, cudaStream_t st) {
+                             int64_t height, cudaStream_t st, const uint32_t* row_idx = nullptr) {
     std::lock_guard<std::mutex> lock(g_bounce.mu);
     int dev = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
@@ -116,8 +120,8 @@ static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int6
     uint8_t* d = static_cast<uint8_t*>(dst);
     const uint8_t* s = static_cast<const uint8_t*>(src);
     for (int t = 1; t < nt; ++t)
-        th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[t]);
-    upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[0]);
+        th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[t]);
+    upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[0]);
     for (auto& x : th) x.join();
     for (int t = 0; t < nt; ++t)
         if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "staged upload from pageable memory");
@@ -173,6 +177,21 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                                   (size_t)width_bytes, (size_t)height, k,
                                   (cudaStream_t)stream));
     return HT_OK;
+}
+
+int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                     const uint32_t* row_idx, int64_t n_rows, void* stream) {
+    if (width_bytes < 0 || n_rows < 0) return ht::bad_arg("ht_copy_rows_h2d: negative extent");
+    if (width_bytes == 0 || n_rows == 0) return HT_OK;
+    if (!dst || !src || !row_idx) return ht::bad_arg("ht_copy_rows_h2d: NULL pointer");
+    if (dst_pitch < width_bytes || src_pitch < width_bytes) return ht::bad_arg("ht_copy_rows_h2d: pitch smaller than width");
+    int dev = 0;
+    HT_CUDA_TRY(cudaGetDevice(&dev));
+    if ((size_t)width_bytes > ht::kBounceBytes || dev >= ht::kMaxBounceDevs) {
+        ht::set_error("ht_copy_rows_h2d: rows of %lld bytes do not fit the bounce buffers", (long long)width_bytes);
+        return HT_ERR_UNSUPPORTED;
+    }
+    return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, n_rows, (cudaStream_t)stream, row_idx);
 }
 
 int ht_host_register(void* ptr, size_t bytes) {

@@ -83,7 +83,22 @@ class DevicePlan:
         )
 
         self._local = None  # (LocalTables, device tensors, ctypes struct), built on first use
+        self._compact = None  # tables for a genotype buffer that holds only the referenced variants
         self._up = up
+
+    def compact_tables(self):
+        """Pack tables for a device buffer whose "columns" are just the plan's referenced variants, in
+        var_col order (what transform_host uploads from a variant-major host array when few of its
+        variants are referred to): variant v sits at column v.  Only the kernels that go through var_col
+        (variant-major, generic) apply, which is what that layout takes anyway."""
+        if self._compact is None:
+            ident = torch.arange(self.plan.n_vars, dtype=torch.int32, device=self.device)
+            tables = _cuda.PackTables(
+                self.plan.n_vars, self.plan.n_vars, self.plan.n_keys, _ptr(ident), _ptr(self.var_key_off),
+                _ptr(self.key_allele), _ptr(self.key_label), None, None, None, None, -1,
+            )
+            self._compact = (ident, tables)
+        return self._compact[1]
 
     n_haps = property(lambda self: self.plan.n_haps)
     n_keys = property(lambda self: self.plan.n_keys)
@@ -136,14 +151,15 @@ def out_pitch(n_haps: int) -> int:
 
 def pack(dplan: DevicePlan, gt_ptr: int, gt_strides, n_samples: int, planes: torch.Tensor,
          anc_ptr: int = 0, anc_strides=(0, 0, 0), flags: torch.Tensor = None,
-         mode: int = _cuda.HT_PACK_AUTO, stream=None) -> None:
-    """K1 on raw device pointers; strides are (sample, variant, strand) in bytes."""
+         mode: int = _cuda.HT_PACK_AUTO, stream=None, tables=None) -> None:
+    """K1 on raw device pointers; strides are (sample, variant, strand) in bytes.  `tables`:
+    DevicePlan.compact_tables() when the buffer holds only the referenced variants."""
     if dplan.plan.has_ancestry != bool(anc_ptr):
         raise ValueError("ancestry plan and ancestry array must be given together")
     check(
         _cuda.lib().ht_pack_u8(
             gt_ptr, *map(int, gt_strides), anc_ptr, *map(int, anc_strides), n_samples,
-            ctypes.byref(dplan.tables), _ptr(planes), _ptr(flags), mode, _stream_ptr(stream),
+            ctypes.byref(tables if tables is not None else dplan.tables), _ptr(planes), _ptr(flags), mode, _stream_ptr(stream),
         ),
         "ht_pack_u8",
     )
@@ -405,11 +421,29 @@ class _HostPipe:
             self.nbuf = nbuf = min(2, len(bounds))
             self.pitch = out_pitch(H)
             ends = sorted(bounds, key=lambda b: b[0] - b[1])[:2] + bounds[-1:]  # the largest chunks (and the last)
-            gt_bytes = max(_region(gt, *b).dev_bytes() for b in ends)
+            # Variant-major host array (VCF reader layout: a variant is a contiguous row) of which the plan
+            # refers to at most half the variants: upload only those rows (ht_copy_rows_h2d) -- the device-side
+            # counterpart of the reference's gts.subset(variants=...) gather (haplotypes.py:1388)
+            r0 = _region(gt, *bounds[0])
+            self.gather = (not r0.sample_major and r0.keep is None and 0 < 2 * plan.n_vars <= self.p
+                           and r0.width <= (8 << 20))
+            self.rows_idx = np.ascontiguousarray(plan.var_col, dtype=np.uint32) if self.gather else None
+            self.pv = plan.n_vars if self.gather else self.p  # variant rows held by the device buffers
+            self.tables = self.dplan.compact_tables() if self.gather else None
+            if self.gather:
+                gt_bytes = max(plan.n_vars * _region(gt, *b).dev_pitch() for b in ends)
+            else:
+                gt_bytes = max(_region(gt, *b).dev_bytes() for b in ends)
             self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.anc_buf = [None] * nbuf
             if plan.has_ancestry:
-                anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in ends)
+                ra0 = _region(ancestry, *bounds[0])
+                if self.gather and (ra0.sample_major or ra0.keep is not None or ra0.width > (8 << 20)):
+                    raise ValueError("ancestry must have the memory layout of the genotypes")
+                if self.gather:
+                    anc_bytes = max(plan.n_vars * _region(ancestry, *b).dev_pitch() for b in ends)
+                else:
+                    anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in ends)
                 self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.out_buf = [torch.empty(chunk * self.pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.planes = alloc_planes(chunk, plan.n_keys, dev)
@@ -435,12 +469,12 @@ class _HostPipe:
                 s_in.wait_event(self.ev_cmp[b])
             rg = _region(self.gt, s0, s1)
             self.keep.append(rg.keep)
-            _copy2d(self.gt_buf[b].data_ptr(), rg.dev_pitch(), rg.ptr, rg.pitch, rg.width, rg.rows, _cuda.HT_COPY_H2D, s_in)
+            self._upload(self.gt_buf[b], rg, s_in)
             ra = None
             if plan.has_ancestry:
                 ra = _region(self.ancestry, s0, s1)
                 self.keep.append(ra.keep)
-                _copy2d(self.anc_buf[b].data_ptr(), ra.dev_pitch(), ra.ptr, ra.pitch, ra.width, ra.rows, _cuda.HT_COPY_H2D, s_in)
+                self._upload(self.anc_buf[b], ra, s_in)
             self.ev_h2d[b] = s_in.record_event()
             # compute (the previous result in this output buffer must have left)
             s_cmp.wait_event(self.ev_h2d[b])
@@ -452,22 +486,22 @@ class _HostPipe:
                 # arrays that interleave the phase column (or other odd strides): dense re-layout
                 # on the device so that the fast pack kernels apply (PCIe is the bound here)
                 if not _fast_layout(g_str):
-                    d_str, d_bytes = rg.dense(rows, p)
+                    d_str, d_bytes = rg.dense(rows, self.pv)
                     if self.dense_gt is None or self.dense_gt.numel() < d_bytes:
                         with torch.cuda.stream(s_cmp):
                             self.dense_gt = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, p, self.dense_gt.data_ptr(),
+                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, self.pv, self.dense_gt.data_ptr(),
                                                     d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
                     g_ptr, g_str = self.dense_gt.data_ptr(), d_str
                 if ra and not _fast_layout(a_str):
-                    d_str, d_bytes = ra.dense(rows, p)
+                    d_str, d_bytes = ra.dense(rows, self.pv)
                     if self.dense_anc is None or self.dense_anc.numel() < d_bytes:
                         with torch.cuda.stream(s_cmp):
                             self.dense_anc = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, p, self.dense_anc.data_ptr(),
+                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, self.pv, self.dense_anc.data_ptr(),
                                                     d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
                     a_ptr, a_str = self.dense_anc.data_ptr(), d_str
-            pack(self.dplan, g_ptr, g_str, rows, self.planes, a_ptr, a_str, None, self.pack_mode, s_cmp)
+            pack(self.dplan, g_ptr, g_str, rows, self.planes, a_ptr, a_str, None, self.pack_mode, s_cmp, tables=self.tables)
             transform_u8(self.dplan, self.planes, rows, self.out_buf[b].data_ptr(), self.pitch, s_cmp)
             self.ev_cmp[b] = s_cmp.record_event()
             # D2H
@@ -475,12 +509,34 @@ class _HostPipe:
             _copy2d(self.out_ptr + s0 * 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, s_out)
             self.ev_d2h[b] = s_out.record_event()
 
+    def _upload(self, buf: torch.Tensor, reg: "_Region", stream) -> None:
+        """Host region -> device buffer with 16-byte aligned rows; in gather mode only the referenced variants."""
+        if self.gather:
+            check(_cuda.lib().ht_copy_rows_h2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
+                                               self.rows_idx.ctypes.data, len(self.rows_idx), stream.cuda_stream),
+                  "ht_copy_rows_h2d")
+        else:
+            _copy2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width, reg.rows, _cuda.HT_COPY_H2D, stream)
+
     def finish(self) -> None:
         with torch.cuda.device(self.dev):
             self.s_out.synchronize()
             self.s_cmp.synchronize()
             self.s_in.synchronize()
             self.cur.wait_stream(self.s_out)
+
+
+def upload_bytes(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None) -> int:
+    """Bytes transform_host copies to the device for these arrays: the bytes a[:, :, :2] spans, or -- for a
+    variant-major array of which the plan refers to at most half the variants -- only the referenced rows."""
+    total = 0
+    for a in (gt, ancestry):
+        if a is None or a.shape[0] == 0:
+            continue
+        r = _region(a, 0, a.shape[0])
+        gather = not r.sample_major and r.keep is None and 0 < 2 * plan.n_vars <= a.shape[1] and r.width <= (8 << 20)
+        total += r.width * (plan.n_vars if gather else r.rows)
+    return int(total)
 
 
 def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,

@@ -356,6 +356,17 @@ int ht_bp_ancestry(const uint64_t* blk_key, const uint8_t* blk_pop, const uint32
  */
 int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
               int64_t width_bytes, int64_t height, int kind, void* stream);
+
+/*
+ * Upload of SELECTED rows of a host matrix: row r of `dst` receives row row_idx[r] (host array) of `src`.
+ * What Genotypes.subset's column gather (genotypes.py:440) amounts to for the variant-major layout of the
+ * VCF reader, where a variant is a contiguous row: only the variants some haplotype refers to cross PCIe
+ * (1000G-scale config: 0.52 GB instead of 5 GB).  Host threads gather the rows into the page-locked bounce
+ * buffers of ht_copy2d, every block leaves with an asynchronous DMA; the call returns when the source has
+ * been read.  Rows must fit a bounce buffer (8 MB).
+ */
+int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                     const uint32_t* row_idx, int64_t n_rows, void* stream);
 int ht_host_register(void* h_ptr, size_t bytes);
 int ht_host_unregister(void* h_ptr);
 

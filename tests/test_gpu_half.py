@@ -213,3 +213,49 @@ def test_sample_major_pack_mappings_vs_oracle(monkeypatch, mapping, kind, n, p, 
                                   pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC if p % 8 == 0 else _cuda.HT_PACK_AUTO)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=f"{mapping}/{kind}")
+
+
+@pytest.mark.parametrize("layout", ["F", "F3"])
+@pytest.mark.parametrize("kind", ["plain", "ancestry"])
+def test_variant_major_host_array_uploads_only_referenced_variants(layout, kind):
+    """transform_host on a variant-major host array (VCF reader layout) whose plan refers to few of the
+    variants: only those rows are uploaded (ht_copy_rows_h2d + DevicePlan.compact_tables), with and without
+    the phase column between the samples' calls, with ancestry, pageable and page-locked sources."""
+    n, p, H = 3000, 4000, 120
+    rng = np.random.default_rng(5 + (kind == "ancestry"))
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.01] = 255
+    used = np.sort(rng.choice(p, size=500, replace=False))  # the haplotypes draw from 500 of the 4,000 variants
+    k = rng.integers(1, 7, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(used, size=int(x), replace=False)) for x in k])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    anc = hap_label = ref_label = None
+    if kind == "ancestry":
+        anc = np.ascontiguousarray(np.repeat(rng.integers(0, 4, size=(n, (p + 6) // 7, 2), dtype=np.uint8), 7, axis=1)[:, :p])
+        hap_label = rng.integers(0, 4, size=H)
+        ref_label = np.repeat(hap_label, k)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, ref_label)
+    assert 2 * plan.n_vars <= p
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    cols = ref_col.astype(np.int64)
+    want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs,
+                              anc[:, cols] if anc is not None else None,
+                              hap_label.astype(np.uint8) if hap_label is not None else None)
+
+    def vm(a):  # the VCF reader's layout: (p, n, 2|3) in memory, seen as (n, p, 2)
+        if layout == "F":
+            return np.ascontiguousarray(a.transpose(1, 0, 2)).transpose(1, 0, 2)
+        f3 = np.ones((p, n, 3), dtype=np.uint8)
+        f3[:, :, :2] = a.transpose(1, 0, 2)
+        return f3.transpose(1, 0, 2)[:, :, :2]
+
+    g, an = vm(gt), (vm(anc) if anc is not None else None)
+    for chunk in (None, 1024):
+        got = engine.transform_host(g, plan, ancestry=an, chunk_samples=chunk)
+        np.testing.assert_array_equal(got, want, err_msg=f"{layout}/{kind} chunk={chunk}")
+    if layout == "F":  # page-locked source: same path (the gather always goes through the bounce buffers)
+        pinned = engine.pinned_empty((p, n, 2))
+        pinned[:] = gt.transpose(1, 0, 2)
+        got = engine.transform_host(pinned.transpose(1, 0, 2), plan, ancestry=an)
+        np.testing.assert_array_equal(got, want)
