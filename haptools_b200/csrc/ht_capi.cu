@@ -96,10 +96,48 @@ void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, cons
     }
     *err = e;
 }
+// worker t of nt of a download into pageable memory: row blocks t, t + nt, ...; the DMA of a block into one
+// bounce buffer is in flight while the previous block is copied out of the other one
+void download_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, const uint8_t* src, int64_t src_pitch,
+                     int64_t width, int64_t height, int64_t rows_per_block, cudaStream_t st, cudaError_t* err) {
+    cudaError_t e = t ? cudaSetDevice(dev) : cudaSuccess;
+    auto drain = [&](int64_t r0, int64_t rows, int b) {  // block (r0, rows) has been asked into buffer b
+        e = cudaEventSynchronize(g_bounce.ev[dev][t][b]);
+        if (e != cudaSuccess) return;
+        const uint8_t* stage = g_bounce.buf[t][b];
+        uint8_t* d = dst + r0 * dst_pitch;
+        if (dst_pitch == width) {
+            memcpy(d, stage, (size_t)(rows * width));
+        } else {
+            for (int64_t r = 0; r < rows; ++r) memcpy(d + r * dst_pitch, stage + r * width, (size_t)width);
+        }
+        g_bounce.last_dev[t][b] = -1;  // free, nothing pending
+    };
+    int b = 0;
+    int64_t prev_r0 = -1, prev_rows = 0;
+    for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
+        const int64_t rows = height - r0 < rows_per_block ? height - r0 : rows_per_block;
+        const int ld = g_bounce.last_dev[t][b];
+        if (ld >= 0) e = cudaEventSynchronize(g_bounce.ev[ld][t][b]);  // an earlier upload out of this buffer
+        if (e != cudaSuccess) break;
+        e = cudaMemcpy2DAsync(g_bounce.buf[t][b], (size_t)width, src + r0 * src_pitch, (size_t)src_pitch, (size_t)width,
+                              (size_t)rows, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[dev][t][b], st);
+        if (e != cudaSuccess) break;
+        g_bounce.last_dev[t][b] = dev;
+        if (prev_r0 >= 0) drain(prev_r0, prev_rows, b ^ 1);
+        prev_r0 = r0;
+        prev_rows = rows;
+    }
+    if (e == cudaSuccess && prev_r0 >= 0) drain(prev_r0, prev_rows, b ^ 1);
+    *err = e;
+}
 }  // namespace
 
+// staged copy between PAGEABLE host memory and the device; `download`: device -> host (returns when the
+// destination holds the data), else host -> device (returns when the source has been read)
 static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
-                             int64_t height, cudaStream_t st, const uint32_t* row_idx = nullptr) {
+                             int64_t height, cudaStream_t st, const uint32_t* row_idx = nullptr, bool download = false) {
     std::lock_guard<std::mutex> lock(g_bounce.mu);
     int dev = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
@@ -119,12 +157,18 @@ static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int6
     th.reserve(nt > 1 ? nt - 1 : 0);
     uint8_t* d = static_cast<uint8_t*>(dst);
     const uint8_t* s = static_cast<const uint8_t*>(src);
-    for (int t = 1; t < nt; ++t)
-        th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[t]);
-    upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[0]);
+    if (download) {
+        for (int t = 1; t < nt; ++t)
+            th.emplace_back(download_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[t]);
+        download_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[0]);
+    } else {
+        for (int t = 1; t < nt; ++t)
+            th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[t]);
+        upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[0]);
+    }
     for (auto& x : th) x.join();
     for (int t = 0; t < nt; ++t)
-        if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "staged upload from pageable memory");
+        if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "staged copy through the bounce buffers");
     return HT_OK;
 }
 
@@ -168,6 +212,14 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
         if (e != cudaSuccess) cudaGetLastError();  // old drivers report unregistered memory as an error
         if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered)
             return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream);
+    }
+    if (kind == HT_COPY_D2H && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes &&
+        cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev < ht::kMaxBounceDevs) {
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, dst);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered)
+            return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream, nullptr, true);
     }
     if (dst_pitch == width_bytes && src_pitch == width_bytes) {  // dense on both sides: one linear copy
         HT_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)width_bytes * (size_t)height, k, (cudaStream_t)stream));

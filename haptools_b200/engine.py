@@ -455,6 +455,7 @@ class _HostPipe:
         self.ev_h2d, self.ev_cmp, self.ev_d2h = [None] * nbuf, [None] * nbuf, [None] * nbuf
         self.keep = []
         self.k = 0
+        self.pending = None  # (buffer, first sample, rows) of the chunk whose result has not been asked for yet
 
     def submit(self, s0: int, s1: int) -> None:
         """Queue chunk [s0, s1) on this device; returns at once (everything is asynchronous)."""
@@ -504,10 +505,22 @@ class _HostPipe:
             pack(self.dplan, g_ptr, g_str, rows, self.planes, a_ptr, a_str, None, self.pack_mode, s_cmp, tables=self.tables)
             transform_u8(self.dplan, self.planes, rows, self.out_buf[b].data_ptr(), self.pitch, s_cmp)
             self.ev_cmp[b] = s_cmp.record_event()
-            # D2H
-            s_out.wait_event(self.ev_cmp[b])
-            _copy2d(self.out_ptr + s0 * 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, s_out)
-            self.ev_d2h[b] = s_out.record_event()
+            # D2H of the PREVIOUS chunk: asked for after this chunk's upload and kernels are queued, because the
+            # copy blocks the host when the result lies in pageable memory (ht_copy2d then moves it through
+            # its bounce buffers on a few host threads)
+            self._download()
+            self.pending = (b, s0, rows)
+
+    def _download(self) -> None:
+        if self.pending is None:
+            return
+        b, s0, rows = self.pending
+        self.pending = None
+        H = self.H
+        with torch.cuda.device(self.dev):
+            self.s_out.wait_event(self.ev_cmp[b])
+            _copy2d(self.out_ptr + s0 * 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, self.s_out)
+            self.ev_d2h[b] = self.s_out.record_event()
 
     def _upload(self, buf: torch.Tensor, reg: "_Region", stream) -> None:
         """Host region -> device buffer with 16-byte aligned rows; in gather mode only the referenced variants."""
@@ -519,6 +532,7 @@ class _HostPipe:
             _copy2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width, reg.rows, _cuda.HT_COPY_H2D, stream)
 
     def finish(self) -> None:
+        self._download()
         with torch.cuda.device(self.dev):
             self.s_out.synchronize()
             self.s_cmp.synchronize()
