@@ -589,8 +589,10 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
     devs = [torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device()) for d in devs]
     if out is None:
         nbytes = n * H * 2
-        if pin_output is None:
-            pin_output = 0 < nbytes <= (4 << 30)
+        # A plain numpy result by default, like the reference's np.empty: page-locking a fresh buffer costs far
+        # more than it saves in ONE call (3.3 GB: 1.66 s to allocate + 63 ms, against 314 ms with the staged
+        # download into pageable memory, profiles/exp_first_call.py).  pin_output=True, or a page-locked `out`
+        # that is reused (bench.py), gives the full PCIe rate.
         out = pinned_empty((n, H, 2)) if pin_output else np.empty((n, H, 2), dtype=np.uint8)
     elif out.shape != (n, H, 2) or out.dtype.itemsize != 1 or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous 1-byte array of shape (n, H, 2)")
