@@ -250,13 +250,52 @@ template <bool kAnc>
 __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, const VmItem<kAnc>& it, int lane) {
     const uint32_t kb = it.kb, ke = it.ke;
 
+    if (a.flags) {
+        uint32_t fl = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fl |= qc_flags4(it.x[j].x) | qc_flags4(it.x[j].y) | qc_flags4(it.x[j].z) | qc_flags4(it.x[j].w);
+        publish_flags(a.flags, fl);
+    }
+    const uint32_t vm = valid_mask(a.n, tile, lane);  // lane l stores word l of a record
+
+    if (!kAnc) {
+        // Biallelic single pass: if the variant's keys are just alleles {0, 1} and no byte of the
+        // row is >= 2, the allele-1 plane is the bytes' low bit and the allele-0 plane its
+        // complement.  A chunk is 4 words x = {s.c0, s.c1, (s+1).c0, (s+1).c1} of 0/1 bytes (samples
+        // 2i, 2i+1 in word i); x * 0x10002 puts the word's two strand-0 bits next to each other at bits
+        // 16, 17 and its two strand-1 bits at 24, 25 (the other partial products land in bits 1 and 9),
+        // and the four words shifted by 2i tile bits 16..23 / 24..31 without a carry: FOUR multiply-adds
+        // turn 16 genotype bytes into the 8 sample bits of both strands (bytes 2 and 3 of r).
+        const uint32_t nk = ke - kb;
+        const uint32_t al0 = nk >= 1 ? __ldg(a.key_allele + kb) : 0u;
+        const uint32_t al1 = nk >= 2 ? __ldg(a.key_allele + kb + 1) : 1u;
+        uint32_t d = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d |= (it.x[j].x | it.x[j].y) | (it.x[j].z | it.x[j].w);
+        const bool dirty = __any_sync(0xffffffffu, (d & 0xfefefefeu) != 0u);
+        if (nk <= 2 && al0 <= 1u && al1 <= 1u && !dirty) {
+            // keys are sorted by allele: (0), (1) or (0, 1)
+            const int k_ref = al0 == 0u ? (int)kb : -1;
+            const int k_alt = al0 == 1u ? (int)kb : (nk == 2 ? (int)kb + 1 : -1);
+            uint32_t r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                r[j] = it.x[j].x * 0x00010002u + it.x[j].y * 0x00040008u + it.x[j].z * 0x00100020u + it.x[j].w * 0x00400080u;
+            const uint32_t t0 = prmt(r[0], r[1], 0x7362), t1 = prmt(r[2], r[3], 0x7362);  // [r0.b2 r1.b2 r0.b3 r1.b3]
+            const uint32_t M0 = prmt(t0, t1, 0x5410);  // byte j = 8 samples of chunk j, strand 0
+            const uint32_t M1 = prmt(t0, t1, 0x7632);  // strand 1
+            const uint32_t w0 = vm_gather_word(M0, lane), w1 = vm_gather_word(M1, lane);
+            if (k_alt >= 0) record(a, tile, (uint32_t)k_alt)[lane] = make_uint2(w0 & vm, w1 & vm);
+            if (k_ref >= 0) record(a, tile, (uint32_t)k_ref)[lane] = make_uint2(~w0 & vm, ~w1 & vm);
+            return;
+        }
+    }
+
     // y = strand-0 bytes, z = strand-1 bytes of the lane's 4 chunks (8 samples each)
     uint32_t y[4][2], z[4][2], ay[4][2], az[4][2];
-    uint32_t fl = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const uint4 x = it.x[j];
-        if (a.flags) fl |= qc_flags4(x.x) | qc_flags4(x.y) | qc_flags4(x.z) | qc_flags4(x.w);
         y[j][0] = prmt(x.x, x.y, 0x6420);
         y[j][1] = prmt(x.z, x.w, 0x6420);
         z[j][0] = prmt(x.x, x.y, 0x7531);
@@ -269,41 +308,6 @@ __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, co
             az[j][1] = prmt(q.z, q.w, 0x7531);
         }
     }
-    publish_flags(a.flags, fl);
-    const uint32_t vm = valid_mask(a.n, tile, lane);  // lane l stores word l of a record
-
-    if (!kAnc) {
-        // Biallelic single pass: if the variant's keys are just alleles {0, 1} and no byte of the
-        // row is >= 2, the allele-1 plane is the bytes' low bit and the allele-0 plane its
-        // complement.  8 samples of a strand are gathered with one carry-free multiply:
-        // u = lsb(s0..s3) | lsb(s4..s7) << 4 has its bits at 8i and 8i + 4; times 0x00204081 they
-        // land contiguously at bits 21..28.
-        const uint32_t nk = ke - kb;
-        const uint32_t al0 = nk >= 1 ? __ldg(a.key_allele + kb) : 0u;
-        const uint32_t al1 = nk >= 2 ? __ldg(a.key_allele + kb + 1) : 1u;
-        uint32_t d = 0u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d |= (y[j][0] | y[j][1]) | (z[j][0] | z[j][1]);
-        const bool dirty = __any_sync(0xffffffffu, (d & 0xfefefefeu) != 0u);
-        if (nk <= 2 && al0 <= 1u && al1 <= 1u && !dirty) {
-            // keys are sorted by allele: (0), (1) or (0, 1)
-            const int k_ref = al0 == 0u ? (int)kb : -1;
-            const int k_alt = al0 == 1u ? (int)kb : (nk == 2 ? (int)kb + 1 : -1);
-            uint32_t M0 = 0u, M1 = 0u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t u0 = (y[j][0] & 0x01010101u) + ((y[j][1] & 0x01010101u) << 4);
-                const uint32_t u1 = (z[j][0] & 0x01010101u) + ((z[j][1] & 0x01010101u) << 4);
-                M0 |= (((u0 * 0x00204081u) >> 21) & 0xffu) << (8 * j);  // 8 samples, strand 0
-                M1 |= (((u1 * 0x00204081u) >> 21) & 0xffu) << (8 * j);  // 8 samples, strand 1
-            }
-            const uint32_t w0 = vm_gather_word(M0, lane), w1 = vm_gather_word(M1, lane);
-            if (k_alt >= 0) record(a, tile, (uint32_t)k_alt)[lane] = make_uint2(w0 & vm, w1 & vm);
-            if (k_ref >= 0) record(a, tile, (uint32_t)k_ref)[lane] = make_uint2(~w0 & vm, ~w1 & vm);
-            return;
-        }
-    }
-
 #pragma unroll 1
     for (uint32_t k = kb; k < ke; ++k) {
         const uint32_t pat = (uint32_t)__ldg(a.key_allele + k) * 0x01010101u;
@@ -325,42 +329,71 @@ __device__ __forceinline__ void pack_vm_item(const PackArgs& a, int64_t tile, co
         record(a, tile, k)[lane] = make_uint2(vm_gather_word(M0, lane) & vm, vm_gather_word(M1, lane) & vm);
     }
 }
+// loop state of a warp of the variant-major kernel.  Items are numbered hi * radix + lo and a warp's items
+// advance by a constant step, so (hi, lo) are stepped without a 64-bit division.  Two orders:
+//   tile-major     hi = tile, lo = variant (radix = n_vars): the 8 warps of a CTA write 8 neighbouring records
+//   variant-major  hi = variant, lo = tile (radix = n_tiles): neighbouring warps read neighbouring 2 KB pieces
+//                  of ONE variant row (a whole 5 KB row at 2,504 samples) -- for cohorts of a few tiles, where
+//                  the tile-major order touches a row once per tile, a DRAM page apart each time
+struct VmWalk {
+    int64_t item, n_items, stride;
+    int32_t radix, step_hi, step_lo, hi_n, lo_n, tile;  // tile: of the current item; *_n: next item
+    bool vfirst;
+    VmIdx ix_n;  // index entries of the next item
+};
+
+// one iteration: the row loads of the next item go out into `nxt`, the index entries of the item after it are
+// asked for, then the current item (`cur`, loaded one iteration ago) is packed.  (Calling it with the two
+// buffers in alternating roles instead of copying nxt to cur costs 268 bytes of spills at 64 registers:
+// 0.189 against 0.125 ms on the 1000G-scale config.)
+template <bool kAnc>
+__device__ __forceinline__ void vm_step(const PackArgs& a, VmWalk& w, int lane, const VmItem<kAnc>& cur, VmItem<kAnc>& nxt) {
+    int32_t hi_nn = w.hi_n + w.step_hi, lo_nn = w.lo_n + w.step_lo;
+    if (lo_nn >= w.radix) {
+        lo_nn -= w.radix;
+        ++hi_nn;
+    }
+    const int32_t tile_n = w.vfirst ? w.lo_n : w.hi_n;
+    VmIdx ix_nn = {0u, 0u, 0u};
+    if (w.item + w.stride < w.n_items) vm_fetch<kAnc>(a, tile_n, w.ix_n, lane, nxt);
+    if (w.item + 2 * w.stride < w.n_items) ix_nn = vm_fetch_idx(a, w.vfirst ? hi_nn : lo_nn);
+    pack_vm_item<kAnc>(a, w.tile, cur, lane);
+    w.tile = tile_n;
+    w.hi_n = hi_nn;
+    w.lo_n = lo_nn;
+    w.ix_n = ix_nn;
+    w.item += w.stride;
+}
+
 template <bool kAnc>
 __global__ void __launch_bounds__(kPackThreads, kAnc ? 2 : 4)
-pack_vm_kernel(const PackArgs a, int64_t n_tiles) {
+pack_vm_kernel(const PackArgs a, int64_t n_tiles, bool vfirst) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_items = n_tiles * a.n_vars, stride = (int64_t)gridDim.x * kPackWarps;
-    int64_t item = (int64_t)blockIdx.x * kPackWarps + warp;
-    if (item >= n_items) return;
-    // (tile, variant) of an item advance by a constant step: no 64-bit division in the loop
-    const int64_t step_t = stride / a.n_vars, step_v = stride % a.n_vars;
-    int64_t tile = item / a.n_vars, v = item % a.n_vars;
-    VmItem<kAnc> cur, nxt;
-    vm_fetch<kAnc>(a, tile, vm_fetch_idx(a, v), lane, cur);
-    // (tile, variant) of the next item, and the index entries of that item (in flight since one iteration)
-    int64_t tile_n = tile + step_t, v_n = v + step_v;
-    if (v_n >= a.n_vars) {
-        v_n -= a.n_vars;
-        ++tile_n;
+    VmWalk w;
+    w.vfirst = vfirst;
+    w.n_items = n_tiles * a.n_vars;
+    w.stride = (int64_t)gridDim.x * kPackWarps;
+    w.item = (int64_t)blockIdx.x * kPackWarps + warp;
+    if (w.item >= w.n_items) return;
+    w.radix = (int32_t)(vfirst ? n_tiles : a.n_vars);
+    w.step_hi = (int32_t)(w.stride / w.radix);
+    w.step_lo = (int32_t)(w.stride % w.radix);
+    const int32_t hi = (int32_t)(w.item / w.radix), lo = (int32_t)(w.item % w.radix);
+    w.tile = vfirst ? lo : hi;
+    VmItem<kAnc> b0, b1;
+    vm_fetch<kAnc>(a, w.tile, vm_fetch_idx(a, vfirst ? hi : lo), lane, b0);
+    w.hi_n = hi + w.step_hi;
+    w.lo_n = lo + w.step_lo;
+    if (w.lo_n >= w.radix) {
+        w.lo_n -= w.radix;
+        ++w.hi_n;
     }
-    VmIdx ix_n = {0u, 0u, 0u};
-    if (item + stride < n_items) ix_n = vm_fetch_idx(a, v_n);
+    w.ix_n = VmIdx{0u, 0u, 0u};
+    if (w.item + w.stride < w.n_items) w.ix_n = vm_fetch_idx(a, vfirst ? w.hi_n : w.lo_n);
 #pragma unroll 1
-    for (; item < n_items; item += stride) {
-        int64_t tile_nn = tile_n + step_t, v_nn = v_n + step_v;
-        if (v_nn >= a.n_vars) {
-            v_nn -= a.n_vars;
-            ++tile_nn;
-        }
-        VmIdx ix_nn = {0u, 0u, 0u};
-        if (item + stride < n_items) vm_fetch<kAnc>(a, tile_n, ix_n, lane, nxt);
-        if (item + 2 * stride < n_items) ix_nn = vm_fetch_idx(a, v_nn);
-        pack_vm_item<kAnc>(a, tile, cur, lane);
-        cur = nxt;
-        tile = tile_n;
-        tile_n = tile_nn;
-        v_n = v_nn;
-        ix_n = ix_nn;
+    while (w.item < w.n_items) {
+        vm_step<kAnc>(a, w, lane, b0, b1);
+        b0 = b1;
     }
 }
 
@@ -1405,9 +1438,21 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
             {
                 const int64_t n_tiles = ht_num_tiles(a.n);
                 const int64_t want = (n_tiles * a.n_vars + kPackWarps - 1) / kPackWarps;
-                const unsigned grid = (unsigned)min(want, (int64_t)148 * 8 * 4);  // a few waves of resident CTAs
-                if (anc) pack_vm_kernel<true><<<grid, kPackThreads, 0, st>>>(a, n_tiles);
-                else pack_vm_kernel<false><<<grid, kPackThreads, 0, st>>>(a, n_tiles);
+                // Grid: whole waves of resident CTAs (4 per SM), about 48 items per warp -- 2 waves on the
+                // 1000G-scale config (103.6 us against 107.1 at 8 and 126.9 at 32), 32 waves at 200 k samples x
+                // 50 k variants (3.69 ms against 3.75 at 8); profiles/exp_pack_vm.py.  HT_VM_WAVES / HT_VM_ORDER
+                // override the choice (measurements, tests).
+                const char* waves_env = getenv("HT_VM_WAVES");
+                const int env_waves = waves_env ? atoi(waves_env) : 0;
+                const int64_t n_items = n_tiles * a.n_vars, wave_warps = (int64_t)148 * 4 * kPackWarps;
+                const int64_t waves = env_waves > 0 ? env_waves : max((int64_t)2, min((int64_t)32, (n_items + 24 * wave_warps) / (48 * wave_warps)));
+                const unsigned grid = (unsigned)min(want, (int64_t)148 * 4 * waves);
+                // Item order: variant-first (neighbouring warps read neighbouring pieces of one variant row) is
+                // faster at every size measured: 107.1 against 114.8 us (1000G-scale), 3.75 against 3.83 ms (200 k)
+                const char* order = getenv("HT_VM_ORDER");  // "t": tile-first
+                const bool vfirst = order ? order[0] != 't' : true;
+                if (anc) pack_vm_kernel<true><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
+                else pack_vm_kernel<false><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
                 HT_CUDA_TRY(cudaGetLastError());
                 return HT_OK;
             }

@@ -215,6 +215,52 @@ def test_sample_major_pack_mappings_vs_oracle(monkeypatch, mapping, kind, n, p, 
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=f"{mapping}/{kind}")
 
 
+@pytest.mark.parametrize("order,waves", [("v", ""), ("t", ""), ("v", "1"), ("t", "1"), ("v", "32")])
+@pytest.mark.parametrize("kind", ["plain", "ancestry"])
+@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1024, 130, 40), (1032, 40, 70), (2504, 600, 200), (5000, 1032, 333)])
+def test_variant_major_pack_item_orders_vs_oracle(monkeypatch, order, waves, kind, n, p, H):
+    """pack_vm_kernel (csrc/ht_pack.cu) walks its (tile, variant) items variant-first (the default) or
+    tile-first, over a grid of 1..32 waves of CTAs (one wave: many items per warp, so the two-items-ahead
+    prefetch runs through every wrap of the walk): both orders against the oracle on ragged shapes with
+    missing and multi-allelic calls."""
+    monkeypatch.setenv("HT_VM_ORDER", order)
+    if waves:
+        monkeypatch.setenv("HT_VM_WAVES", waves)
+    from haptools_b200 import _cuda
+
+    rng = np.random.default_rng(17 * n + p + H)
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.01] = 255
+    gt[rng.random((n, p, 2)) < 0.01] = 2
+    k = rng.integers(0, min(6, p) + 1, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, dtype=np.int64)])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    anc = hap_label = ref_label = None
+    if kind == "ancestry":
+        anc = np.ascontiguousarray(np.repeat(rng.integers(0, 5, size=(n, (p + 6) // 7, 2), dtype=np.uint8), 7, axis=1)[:, :p])
+        hap_label = rng.integers(0, 5, size=H)
+        ref_label = np.repeat(hap_label, k)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, ref_label)
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    cols = ref_col.astype(np.int64)
+    want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs,
+                              anc[:, cols] if anc is not None else None,
+                              hap_label.astype(np.uint8) if hap_label is not None else None)
+
+    def vm(a):  # variant-major on the device, rows padded to 16 bytes
+        pitch = (2 * n + 15) // 16 * 16
+        buf = torch.zeros((p, pitch), dtype=torch.uint8, device="cuda")
+        buf[:, : 2 * n] = torch.from_numpy(np.ascontiguousarray(a.transpose(1, 0, 2)).reshape(p, 2 * n)).cuda()
+        return buf[:, : 2 * n].unflatten(1, (n, 2)).permute(1, 0, 2)
+
+    dplan = engine.DevicePlan(plan)
+    out = engine.transform_device(vm(gt), dplan, ancestry=vm(anc) if anc is not None else None,
+                                  pack_mode=_cuda.HT_PACK_VARIANT_MAJOR)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=f"{order}/{waves}/{kind}")
+
+
 @pytest.mark.parametrize("layout", ["F", "F3"])
 @pytest.mark.parametrize("kind", ["plain", "ancestry"])
 def test_variant_major_host_array_uploads_only_referenced_variants(layout, kind):
