@@ -172,6 +172,68 @@ static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int6
     return HT_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Row gather straight out of PAGE-LOCKED host memory: the SMs read the selected rows over PCIe (mapped
+// host memory, unified addressing) and write them to the device buffer -- no host thread touches a byte
+// and the call is asynchronous on the stream.  A warp per row, 16-byte loads, four in flight per lane.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(uint8_t* __restrict__ dst, int64_t dst_pitch,
+                                                          const uint8_t* __restrict__ src, int64_t src_pitch,
+                                                          int64_t width, const uint32_t* __restrict__ row_idx,
+                                                          int64_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n16 = width >> 4;
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps) {
+        const uint8_t* srow = src + (int64_t)row_idx[r] * src_pitch;
+        uint8_t* drow = dst + r * dst_pitch;
+        const uint4* s = reinterpret_cast<const uint4*>(srow);
+        uint4* d = reinterpret_cast<uint4*>(drow);
+        int64_t i = lane;
+        for (; i + 96 < n16; i += 128) {
+            const uint4 v0 = s[i], v1 = s[i + 32], v2 = s[i + 64], v3 = s[i + 96];
+            d[i] = v0;
+            d[i + 32] = v1;
+            d[i + 64] = v2;
+            d[i + 96] = v3;
+        }
+        for (; i < n16; i += 32) d[i] = s[i];
+        const int64_t t0 = n16 << 4;  // the last width % 16 bytes
+        if (t0 + lane < width) drow[t0 + lane] = srow[t0 + lane];
+    }
+}
+
+// true if the rows were gathered by the kernel; false: the source is not page-locked / not 16-byte aligned
+static int gather_rows_from_pinned(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                                   const uint32_t* row_idx, int64_t n_rows, cudaStream_t st, bool* done) {
+    *done = false;
+    const char* mode = getenv("HT_GATHER");  // "bounce": always the host threads (measurements, tests)
+    if (mode && mode[0] == 'b') return HT_OK;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) {
+        cudaGetLastError();
+        return HT_OK;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return HT_OK;
+    const uint8_t* dsrc = static_cast<const uint8_t*>(at.devicePointer);
+    if (((uintptr_t)dsrc | (uintptr_t)dst | (uintptr_t)src_pitch | (uintptr_t)dst_pitch) & 15) return HT_OK;
+    // the row indices in stream order: allocated, filled, used and freed on `st`
+    uint32_t* d_idx = nullptr;
+    HT_CUDA_TRY(cudaMallocAsync((void**)&d_idx, sizeof(uint32_t) * (size_t)n_rows, st));
+    cudaError_t e = cudaMemcpyAsync(d_idx, row_idx, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const int64_t ctas = (n_rows + 7) / 8;
+        const unsigned grid = (unsigned)(ctas < 148 * 8 ? ctas : 148 * 8);
+        gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<uint8_t*>(dst), dst_pitch, dsrc, src_pitch, width, d_idx, n_rows);
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(d_idx, st);
+    if (e != cudaSuccess) return cuda_fail(e, "row gather from page-locked host memory");
+    HT_CUDA_TRY(ef);
+    *done = true;
+    return HT_OK;
+}
+
 }  // namespace ht
 
 extern "C" {
@@ -239,6 +301,10 @@ int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_
     if (dst_pitch < width_bytes || src_pitch < width_bytes) return ht::bad_arg("ht_copy_rows_h2d: pitch smaller than width");
     int dev = 0;
     HT_CUDA_TRY(cudaGetDevice(&dev));
+    bool done = false;  // page-locked source: the SMs gather the rows over PCIe, asynchronously
+    if (int rc = ht::gather_rows_from_pinned(dst, dst_pitch, src, src_pitch, width_bytes, row_idx, n_rows, (cudaStream_t)stream, &done))
+        return rc;
+    if (done) return HT_OK;
     if ((size_t)width_bytes > ht::kBounceBytes || dev >= ht::kMaxBounceDevs) {
         ht::set_error("ht_copy_rows_h2d: rows of %lld bytes do not fit the bounce buffers", (long long)width_bytes);
         return HT_ERR_UNSUPPORTED;

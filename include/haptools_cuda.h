@@ -364,9 +364,13 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
  * Upload of SELECTED rows of a host matrix: row r of `dst` receives row row_idx[r] (host array) of `src`.
  * What Genotypes.subset's column gather (genotypes.py:440) amounts to for the variant-major layout of the
  * VCF reader, where a variant is a contiguous row: only the variants some haplotype refers to cross PCIe
- * (1000G-scale config: 0.52 GB instead of 5 GB).  Host threads gather the rows into the page-locked bounce
- * buffers of ht_copy2d, every block leaves with an asynchronous DMA; the call returns when the source has
- * been read.  Rows must fit a bounce buffer (8 MB).
+ * (1000G-scale config: 0.52 GB instead of 5 GB).  A PAGE-LOCKED source with 16-byte aligned rows (and dst) is
+ * gathered by a kernel whose warps read the rows straight out of host memory over PCIe: asynchronous on
+ * `stream`, no host thread touches a byte, the source must stay valid until the stream gets there (the
+ * indices are copied during the call).  Any other source: host threads gather the rows into the page-locked
+ * bounce buffers of ht_copy2d, every block leaves with an asynchronous DMA, the call returns when the source
+ * has been read, and rows must fit a bounce buffer (8 MB).  HT_GATHER=bounce in the environment forces the
+ * second way (measurements, tests).
  */
 int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
                      const uint32_t* row_idx, int64_t n_rows, void* stream);
