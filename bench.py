@@ -462,7 +462,7 @@ def run_b200(args):
         # never holds more than one slice's equality array (1.6 GB at the UKB-scale plan)
         ns_total = args.cpu_samples or 8192
         ns = min(ns_total, 2048)
-        n_slices = max(1, ns_total // ns)
+        n_slices = max(1, min(ns_total // ns, -(-n // ns)))  # never more slices than the shard has samples for
         arrays, hap_label = _oracle_plan_arrays(w, H)
         wall = sum(_cpu_slice((w, arrays, 10_000 * i, ns, hap_label))[0] for i in range(n_slices))
         v = n_slices * ns * H * 2 / wall
