@@ -64,3 +64,28 @@ def test_numpy_splitmix_matches_c_constant():
     from haptools_b200 import synth
 
     assert int(synth.splitmix64(np.uint64(0))) == 0xE220A8397B1DCDAF
+
+
+def test_variant_major_multiply_gather_constants_exhaustive():
+    """pack_vm_item's biallelic path (csrc/ht_pack.cu): four multiply-adds turn 16 genotype bytes of 0/1
+    (8 samples x 2 interleaved strands) into the 8 strand-0 bits (byte 2 of the sum) and the 8 strand-1
+    bits (byte 3).  The constants are read out of the kernel source and checked on all 2^16 inputs."""
+    import re
+
+    import numpy as np
+
+    text = (REPO / "haptools_b200" / "csrc" / "ht_pack.cu").read_text()
+    m = re.search(r"r\[j\] = it\.x\[j\]\.x \* (0x[0-9a-fA-F]+)u \+ it\.x\[j\]\.y \* (0x[0-9a-fA-F]+)u \+ "
+                  r"it\.x\[j\]\.z \* (0x[0-9a-fA-F]+)u \+ it\.x\[j\]\.w \* (0x[0-9a-fA-F]+)u;", text)
+    assert m, "the multiply-gather statement of pack_vm_item was not found"
+    consts = [int(c, 16) for c in m.groups()]
+    codes = np.arange(1 << 16, dtype=np.uint32)
+    bits = ((codes[:, None] >> np.arange(16, dtype=np.uint32)) & 1).astype(np.uint8)  # byte i of the chunk
+    words = np.ascontiguousarray(bits).view("<u4").astype(np.uint64)                  # (65536, 4)
+    r = np.zeros(len(codes), dtype=np.uint64)
+    for i, c in enumerate(consts):
+        r = (r + words[:, i] * np.uint64(c)) & np.uint64(0xFFFFFFFF)
+    strand0 = sum(bits[:, 2 * s].astype(np.uint64) << np.uint64(s) for s in range(8))
+    strand1 = sum(bits[:, 2 * s + 1].astype(np.uint64) << np.uint64(s) for s in range(8))
+    np.testing.assert_array_equal((r >> np.uint64(16)) & np.uint64(0xFF), strand0)
+    np.testing.assert_array_equal((r >> np.uint64(24)) & np.uint64(0xFF), strand1)
