@@ -1,5 +1,6 @@
 """Variant-major pack (pack_vm_kernel): time per launch on the 1000G-scale shape and at 200 k samples.
-Run with HT_VM_WAVES=1|2|4|8|16 (grid = that many waves of resident CTAs) or HT_LIB_PATH=<another build>."""
+Run with HT_VM_WAVES=1|2|4|8|16 (grid = that many waves of resident CTAs) or HT_LIB_PATH=<another build>;
+`small` as the first argument: only the 1000G-scale shape with 20 launches (for ncu captures)."""
 import sys, torch
 sys.path.insert(0, ".")
 from haptools_b200 import engine, synth, _cuda
@@ -12,7 +13,10 @@ def timeit(fn, reps):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-for n, p, H, reps in ((2_504, 1_000_000, 10_000, 200), (200_000, 50_000, 100_000, 5)):
+CASES = ((2_504, 1_000_000, 10_000, 200), (200_000, 50_000, 100_000, 5))
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    CASES = ((2_504, 1_000_000, 10_000, 20),)
+for n, p, H, reps in CASES:
     plan = synth.synth_plan(p, H, seed=1)
     dp = engine.DevicePlan(plan)
     planes = engine.alloc_planes(n, plan.n_keys, dev)
