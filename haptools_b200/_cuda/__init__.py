@@ -12,7 +12,7 @@ import os
 
 # HT_LIB_PATH lets experiments (profiles/) load an alternative build of the same ABI
 LIB_PATH = Path(os.environ.get("HT_LIB_PATH") or Path(__file__).resolve().parent / "libhaptools_cuda.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
 HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
@@ -71,6 +71,17 @@ SIGNATURES = {
     "ht_copy_rows_h2d": (_i32, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "ht_host_register": (_i32, [_p, _sz]),
     "ht_host_unregister": (_i32, [_p]),
+    "ht_rowbits_pitch": (_i64, [_i64]),
+    "ht_bits_to_rowbits": (_i32, [_p, _i64, _i64, _p, _i64, _p]),
+    "ht_host_submit_upload": (_i64, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
+    "ht_host_submit_download": (_i64, [_p, _i64, _p, _i64, _i64, _i64, _p]),
+    "ht_host_submit_download_expand": (_i64, [_p, _i64, _i64, _p, _i64, _i64, _p]),
+    "ht_host_wait": (_i32, [_i64]),
+    "ht_host_workers": (_i32, []),
+    "ht_host_is_pageable": (_i32, [_p]),
+    "ht_expand_rowbits_host": (_i32, [_p, _i64, _i64, _i64, _p, _i64]),
+    "ht_host_expand_isa": (_i32, [_i32]),
+    "ht_qc_u8": (_i32, [_p, _i64, _i64, _i64, _i32, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

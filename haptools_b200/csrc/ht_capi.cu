@@ -5,10 +5,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
-#include <thread>
-#include <vector>
-
 #include "ht_common.cuh"
 
 namespace ht {
@@ -33,143 +29,33 @@ int bad_arg(const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Upload from PAGEABLE host memory (what `gts.data` is when it comes out of cyvcf2 / pgenlib /
-// numpy).  cudaMemcpy2DAsync stages such a source through the driver's own bounce buffer with one
-// host thread (11 GB/s on the B200 box); here a few host threads copy row blocks into a ring of
-// page-locked bounce buffers and every block leaves with an asynchronous DMA, so the upload runs
-// at what memcpy on several cores and the PCIe link deliver (HT_HOST_COPY_THREADS, default 4; every
-// thread owns two 8 MB bounce buffers and whole row blocks).  Pure data movement: no byte is
-// interpreted on the host.
+// Copies between PAGEABLE host memory and the device go through the host copy engine (ht_hostcopy.cu: a
+// persistent pool of host threads with page-locked staging slots); the synchronous forms here are
+// submit + wait.  cudaMemcpy2DAsync would stage such memory through the driver's own bounce buffer with one
+// host thread (11 GB/s up, 17.6 GB/s down on the B200 box).
 // ---------------------------------------------------------------------------------------
-namespace {
-constexpr int kMaxCopyThreads = 8, kBufsPerThread = 2;
-constexpr size_t kBounceBytes = 8u << 20;
-constexpr int kMaxBounceDevs = 16;
-struct Bounce {
-    std::mutex mu;  // one staged upload at a time per process
-    uint8_t* buf[kMaxCopyThreads][kBufsPerThread] = {};
-    cudaEvent_t ev[kMaxBounceDevs][kMaxCopyThreads][kBufsPerThread] = {};  // an event belongs to a device
-    int last_dev[kMaxCopyThreads][kBufsPerThread];                          // device of the buffer's last DMA, -1: none
-    Bounce() {
-        for (auto& row : last_dev)
-            for (int& v : row) v = -1;
-    }
-};
-Bounce g_bounce;
+namespace hostcopy {
+enum Kind { kUpload = 0, kDownload = 1, kDownloadExpand = 2 };
+constexpr size_t kSlotBytes = 8u << 20;
+constexpr int kMaxDevs = 16;
+int64_t submit(int kind, void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+               int64_t out_width, const uint32_t* row_idx, cudaStream_t st);
+int wait(int64_t ticket);
+}  // namespace hostcopy
 
-int host_threads() {
-    static const int n = [] {
-        const char* e = getenv("HT_HOST_COPY_THREADS");
-        int v = e ? atoi(e) : 4;
-        const int hw = (int)std::thread::hardware_concurrency();
-        if (hw > 0 && v > hw) v = hw;
-        return v < 1 ? 1 : (v > kMaxCopyThreads ? kMaxCopyThreads : v);
-    }();
-    return n;
+static int staged_copy(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+                       cudaStream_t st, const uint32_t* row_idx = nullptr, bool download = false) {
+    const int64_t ticket = hostcopy::submit(download ? hostcopy::kDownload : hostcopy::kUpload, dst, dst_pitch, src,
+                                            src_pitch, width, height, 0, row_idx, st);
+    if (ticket < 0) return HT_ERR_CUDA;
+    return hostcopy::wait(ticket);
 }
 
-// worker t of nt: row blocks t, t + nt, ... through its own pair of bounce buffers
-// `row_idx` (optional): output row r is source row row_idx[r] (a gather of selected rows)
-void upload_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, const uint8_t* src, int64_t src_pitch,
-                   int64_t width, int64_t height, int64_t rows_per_block, const uint32_t* row_idx, cudaStream_t st,
-                   cudaError_t* err) {
-    cudaError_t e = t ? cudaSetDevice(dev) : cudaSuccess;  // a new host thread starts on device 0
-    int b = 0;
-    for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
-        const int64_t rows = height - r0 < rows_per_block ? height - r0 : rows_per_block;
-        const int ld = g_bounce.last_dev[t][b];
-        if (ld >= 0) e = cudaEventSynchronize(g_bounce.ev[ld][t][b]);  // its last DMA (on any device) has left
-        if (e != cudaSuccess) break;
-        uint8_t* stage = g_bounce.buf[t][b];
-        const uint8_t* s = src + r0 * src_pitch;
-        if (row_idx) {
-            for (int64_t r = 0; r < rows; ++r) memcpy(stage + r * width, src + (int64_t)row_idx[r0 + r] * src_pitch, (size_t)width);
-        } else if (src_pitch == width) {
-            memcpy(stage, s, (size_t)(rows * width));
-        } else {
-            for (int64_t r = 0; r < rows; ++r) memcpy(stage + r * width, s + r * src_pitch, (size_t)width);
-        }
-        e = cudaMemcpy2DAsync(dst + r0 * dst_pitch, (size_t)dst_pitch, stage, (size_t)width, (size_t)width, (size_t)rows,
-                              cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[dev][t][b], st);
-        g_bounce.last_dev[t][b] = e == cudaSuccess ? dev : -1;
-    }
-    *err = e;
-}
-// worker t of nt of a download into pageable memory: row blocks t, t + nt, ...; the DMA of a block into one
-// bounce buffer is in flight while the previous block is copied out of the other one
-void download_blocks(int t, int nt, int dev, uint8_t* dst, int64_t dst_pitch, const uint8_t* src, int64_t src_pitch,
-                     int64_t width, int64_t height, int64_t rows_per_block, cudaStream_t st, cudaError_t* err) {
-    cudaError_t e = t ? cudaSetDevice(dev) : cudaSuccess;
-    auto drain = [&](int64_t r0, int64_t rows, int b) {  // block (r0, rows) has been asked into buffer b
-        e = cudaEventSynchronize(g_bounce.ev[dev][t][b]);
-        if (e != cudaSuccess) return;
-        const uint8_t* stage = g_bounce.buf[t][b];
-        uint8_t* d = dst + r0 * dst_pitch;
-        if (dst_pitch == width) {
-            memcpy(d, stage, (size_t)(rows * width));
-        } else {
-            for (int64_t r = 0; r < rows; ++r) memcpy(d + r * dst_pitch, stage + r * width, (size_t)width);
-        }
-        g_bounce.last_dev[t][b] = -1;  // free, nothing pending
-    };
-    int b = 0;
-    int64_t prev_r0 = -1, prev_rows = 0;
-    for (int64_t r0 = t * rows_per_block; e == cudaSuccess && r0 < height; r0 += nt * rows_per_block, b ^= 1) {
-        const int64_t rows = height - r0 < rows_per_block ? height - r0 : rows_per_block;
-        const int ld = g_bounce.last_dev[t][b];
-        if (ld >= 0) e = cudaEventSynchronize(g_bounce.ev[ld][t][b]);  // an earlier upload out of this buffer
-        if (e != cudaSuccess) break;
-        e = cudaMemcpy2DAsync(g_bounce.buf[t][b], (size_t)width, src + r0 * src_pitch, (size_t)src_pitch, (size_t)width,
-                              (size_t)rows, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaEventRecord(g_bounce.ev[dev][t][b], st);
-        if (e != cudaSuccess) break;
-        g_bounce.last_dev[t][b] = dev;
-        if (prev_r0 >= 0) drain(prev_r0, prev_rows, b ^ 1);
-        prev_r0 = r0;
-        prev_rows = rows;
-    }
-    if (e == cudaSuccess && prev_r0 >= 0) drain(prev_r0, prev_rows, b ^ 1);
-    *err = e;
-}
-}  // namespace
-
-// staged copy between PAGEABLE host memory and the device; `download`: device -> host (returns when the
-// destination holds the data), else host -> device (returns when the source has been read)
-static int h2d_from_pageable(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
-                             int64_t height, cudaStream_t st, const uint32_t* row_idx = nullptr, bool download = false) {
-    std::lock_guard<std::mutex> lock(g_bounce.mu);
-    int dev = 0;
-    HT_CUDA_TRY(cudaGetDevice(&dev));
-    const int64_t rows_per_block = (int64_t)(kBounceBytes / (size_t)width);
-    const int64_t n_blocks = (height + rows_per_block - 1) / rows_per_block;
-    const int nt = (int)(n_blocks < host_threads() ? n_blocks : host_threads());
-    for (int t = 0; t < nt; ++t) {
-        for (int b = 0; b < kBufsPerThread; ++b) {
-            if (!g_bounce.buf[t][b])
-                HT_CUDA_TRY(cudaHostAlloc((void**)&g_bounce.buf[t][b], kBounceBytes, cudaHostAllocPortable));
-            if (!g_bounce.ev[dev][t][b])
-                HT_CUDA_TRY(cudaEventCreateWithFlags(&g_bounce.ev[dev][t][b], cudaEventDisableTiming));
-        }
-    }
-    cudaError_t errs[kMaxCopyThreads] = {};  // cudaSuccess
-    std::vector<std::thread> th;
-    th.reserve(nt > 1 ? nt - 1 : 0);
-    uint8_t* d = static_cast<uint8_t*>(dst);
-    const uint8_t* s = static_cast<const uint8_t*>(src);
-    if (download) {
-        for (int t = 1; t < nt; ++t)
-            th.emplace_back(download_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[t]);
-        download_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, st, &errs[0]);
-    } else {
-        for (int t = 1; t < nt; ++t)
-            th.emplace_back(upload_blocks, t, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[t]);
-        upload_blocks(0, nt, dev, d, dst_pitch, s, src_pitch, width, height, rows_per_block, row_idx, st, &errs[0]);
-    }
-    for (auto& x : th) x.join();
-    for (int t = 0; t < nt; ++t)
-        if (errs[t] != cudaSuccess) return cuda_fail(errs[t], "staged copy through the bounce buffers");
-    return HT_OK;
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) cudaGetLastError();  // old drivers report unregistered memory as an error
+    return e != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -267,22 +153,11 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
         default: return ht::bad_arg("ht_copy2d: unknown kind");
     }
     int cur_dev = 0;
-    if (kind == HT_COPY_H2D && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes &&
-        cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev < ht::kMaxBounceDevs) {
-        cudaPointerAttributes at;
-        const cudaError_t e = cudaPointerGetAttributes(&at, src);
-        if (e != cudaSuccess) cudaGetLastError();  // old drivers report unregistered memory as an error
-        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered)
-            return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream);
-    }
-    if (kind == HT_COPY_D2H && width_bytes * height >= (4 << 20) && (size_t)width_bytes <= ht::kBounceBytes &&
-        cudaGetDevice(&cur_dev) == cudaSuccess && cur_dev < ht::kMaxBounceDevs) {
-        cudaPointerAttributes at;
-        const cudaError_t e = cudaPointerGetAttributes(&at, dst);
-        if (e != cudaSuccess) cudaGetLastError();
-        if (e != cudaSuccess || at.type == cudaMemoryTypeUnregistered)
-            return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream, nullptr, true);
-    }
+    if ((kind == HT_COPY_H2D || kind == HT_COPY_D2H) && width_bytes * height >= (4 << 20) &&
+        (size_t)width_bytes <= ht::hostcopy::kSlotBytes && cudaGetDevice(&cur_dev) == cudaSuccess &&
+        cur_dev < ht::hostcopy::kMaxDevs && ht::is_pageable(kind == HT_COPY_H2D ? src : dst))
+        return ht::staged_copy(dst, dst_pitch, src, src_pitch, width_bytes, height, (cudaStream_t)stream, nullptr,
+                               kind == HT_COPY_D2H);
     if (dst_pitch == width_bytes && src_pitch == width_bytes) {  // dense on both sides: one linear copy
         HT_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)width_bytes * (size_t)height, k, (cudaStream_t)stream));
         return HT_OK;
@@ -305,11 +180,11 @@ int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_
     if (int rc = ht::gather_rows_from_pinned(dst, dst_pitch, src, src_pitch, width_bytes, row_idx, n_rows, (cudaStream_t)stream, &done))
         return rc;
     if (done) return HT_OK;
-    if ((size_t)width_bytes > ht::kBounceBytes || dev >= ht::kMaxBounceDevs) {
-        ht::set_error("ht_copy_rows_h2d: rows of %lld bytes do not fit the bounce buffers", (long long)width_bytes);
+    if ((size_t)width_bytes > ht::hostcopy::kSlotBytes || dev >= ht::hostcopy::kMaxDevs) {
+        ht::set_error("ht_copy_rows_h2d: rows of %lld bytes do not fit the staging slots", (long long)width_bytes);
         return HT_ERR_UNSUPPORTED;
     }
-    return ht::h2d_from_pageable(dst, dst_pitch, src, src_pitch, width_bytes, n_rows, (cudaStream_t)stream, row_idx);
+    return ht::staged_copy(dst, dst_pitch, src, src_pitch, width_bytes, n_rows, (cudaStream_t)stream, row_idx);
 }
 
 int ht_host_register(void* ptr, size_t bytes) {

@@ -95,20 +95,121 @@ class Genotypes:
     def _take(self, idx, axis):
         self.data = self.data[idx, :] if axis == 0 else self.data[:, idx]
 
-    def check_phase(self):
-        """Drop the phase column (haptools/data/genotypes.py:530-557): raises if an
-        unphased heterozygote is present, else keeps a strided view of the two strands."""
-        if self.data.shape[2] < 3:
+    # ---- QC: the reference's numpy passes over the whole matrix run as ONE device pass
+    # (engine.qc_host -> ht_qc_u8); messages, log lines and side effects are the reference's ----------------
+    _MISSING_MIN = 254  # Genotypes.check_missing: >= max(uint8) - 1 (genotypes.py:463)
+
+    def qc(self):
+        """One device pass over ``self.data``: an engine.QCResult with everything the four checks need
+        (a caller that runs several of them on unchanged data can pass it on as ``qc=``)."""
+        from .. import engine
+
+        return engine.qc_host(self.data, missing_min=self._MISSING_MIN)
+
+    def _variant_fields(self, v: int):
+        return tuple(self.variants[v])[:3]
+
+    def check_missing(self, discard_also=False, qc=None):
+        """haptools/data/genotypes.py:444-485."""
+        qc = qc or self.qc()
+        if qc.first_missing is not None:
+            if discard_also:
+                self._discard_samples(np.nonzero(qc.samp_missing)[0])
+            else:
+                s, v = qc.first_missing
+                raise ValueError(
+                    "Genotype with ID {} at POS {}:{} is missing for sample {}".format(
+                        *self._variant_fields(v), self.samples[s]
+                    )
+                )
+        if discard_also and not self.data.shape[0]:
+            self.log.warning(
+                "All samples were discarded! Check that that none of your variants are"
+                " missing genotypes (GT: '.|.')."
+            )
+
+    def _discard_samples(self, samp_idx, level: str = "warning"):
+        original_num_samples = len(self.samples)
+        self.data = np.delete(self.data, samp_idx, axis=0)
+        self.samples = tuple(np.delete(self.samples, samp_idx))
+        getattr(self.log, level)(
+            "Ignoring missing genotypes from "
+            f"{original_num_samples - len(self.samples)} samples"
+        )
+        self._samp_idx = None
+
+    def check_biallelic(self, discard_also=False, qc=None):
+        """haptools/data/genotypes.py:487-528 (turns ``data`` into bool)."""
+        if self.data.dtype == np.bool_:
+            self.log.warning("All genotypes are already biallelic")
+            return
+        qc = qc or self.qc()
+        if qc.first_multiallelic is not None:
+            if discard_also:
+                variant_idx = np.nonzero(qc.var_multiallelic)[0]
+                # the reference counts (sample, variant) PAIRS here (len of np.nonzero's second array)
+                self.log.info(f"Ignoring {qc.n_multiallelic} multiallelic variants")
+                self.data = np.delete(self.data, variant_idx, axis=1)
+                self.variants = np.delete(self.variants, variant_idx)
+                self._var_idx = None
+            else:
+                s, v = qc.first_multiallelic
+                raise ValueError(
+                    "Variant with ID {} at POS {}:{} is multiallelic for sample {}".format(
+                        *self._variant_fields(v), self.samples[s]
+                    )
+                )
+        if discard_also and not self.data.shape[1]:
+            self.log.warning(
+                "All variants were discarded! Check that there are biallelic variants "
+                "in your dataset."
+            )
+        self.data = self.data.astype(np.bool_)
+
+    def check_phase(self, qc=None):
+        """Drop the phase column (haptools/data/genotypes.py:530-557): raises if an unphased heterozygote
+        -- ``(bool(g0) ^ bool(g1)) & ~bool(phase)`` -- is present, else keeps a strided view of the two
+        strands."""
+        if self._prephased or self.data.shape[2] < 3:
             self.log.warning("Phase information has already been removed from the data")
             return
-        het_unphased = np.logical_and(self.data[:, :, 0] != self.data[:, :, 1], ~self.data[:, :, 2].astype(bool))
-        if het_unphased.any():
-            s, v = np.argwhere(het_unphased)[0]
+        qc = qc or self.qc()
+        if qc.first_unphased is not None:
+            s, v = qc.first_unphased
             raise ValueError(
-                f"Variant with ID {self.variants['id'][v]} at POS {self.variants['chrom'][v]}:"
-                f"{self.variants['pos'][v]} is unphased for sample {self.samples[s]}"
+                "Variant with ID {} at POS {}:{} is unphased for sample {}".format(
+                    *self._variant_fields(v), self.samples[s]
+                )
             )
         self.data = self.data[:, :, :2]
+
+    def check_maf(self, threshold: float = None, discard_also: bool = False, warn_only: bool = False, qc=None):
+        """haptools/data/genotypes.py:559-625; returns the minor allele frequency of every variant."""
+        qc = qc or self.qc()
+        maf = qc.maf()
+        if threshold is None:
+            return maf
+        rare_variants = maf < threshold
+        if np.any(rare_variants):
+            idx = np.nonzero(rare_variants)[0]
+            if discard_also:
+                original_num_variants = len(self.variants)
+                self.data = np.delete(self.data, idx, axis=1)
+                self.variants = np.delete(self.variants, idx)
+                maf = np.delete(maf, idx)
+                self.log.info(
+                    f"Ignoring {original_num_variants - len(self.variants)} variants "
+                    f"with MAF < {threshold}"
+                )
+                self._var_idx = None
+            else:
+                vals = self._variant_fields(idx[0]) + (maf[idx[0]], threshold)
+                msg = "Variant with ID {} at POS {}:{} has MAF {} < {}".format(*vals)
+                if warn_only:
+                    self.log.warning(msg)
+                else:
+                    raise ValueError(msg)
+        return maf
 
 
 class GenotypesVCF(Genotypes):

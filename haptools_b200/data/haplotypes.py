@@ -81,7 +81,9 @@ class Haplotype:
         from .. import engine
         from ..plan import plan_from_haplotypes
 
-        plan = plan_from_haplotypes([self], genotypes, ancestry=False, who=f"haplotype '{self.id}'")
+        # clip_bool=False: this form compares an INTEGER allele array (haplotypes.py:499-511), so with bool
+        # genotypes an allele index >= 2 never matches (the plural form's dtype=bool cast does not apply)
+        plan = plan_from_haplotypes([self], genotypes, ancestry=False, who=f"haplotype '{self.id}'", clip_bool=False)
         _reject_empty(self, genotypes)
         return engine.transform_host(genotypes.data, plan)[:, 0]
 
@@ -129,8 +131,15 @@ class Haplotypes:
         variants["pos"] = [hap.start for hap in haps]
         variants["alleles"].fill(("A", "T"))
         hap_gts.variants = variants
-        plan = plan_from_haplotypes(haps, gts, ancestry=ancestry)
-        self.log.debug(f"Packing genotypes for {plan.n_keys} distinct alleles")
+        # the five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order (the first
+        # two are emitted by the planner at the steps they belong to)
+        plan = plan_from_haplotypes(haps, gts, ancestry=ancestry, log=self.log)
+        self.log.info(f"Transforming genotypes for {len(haps)} haplotypes")
+        self.log.debug(
+            f"Allocating array with dtype {gts.data.dtype} and size "
+            f"{(len(gts.samples), len(haps), 2)}"
+        )
+        self.log.debug("Computing haplotype genotypes. This may take a while")
         if ancestry and gts.data.shape[2] != 2:
             # haptools/transform.py:137 compares the whole last axis; a leftover phase column
             # makes the reference fail with a broadcast error -- same exception class here
@@ -138,7 +147,6 @@ class Haplotypes:
                 f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
                 f"into shape {(gts.data.shape[0], 2)}"
             )
-        self.log.info(f"Transforming genotypes for {len(haps)} haplotypes")
         hap_gts.data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
         return hap_gts
 

@@ -31,6 +31,9 @@ TILE = _cuda.TILE_SAMPLES
 # section 5) it does not beat the one-kernel form yet (12.7 vs 10.1 ms on the UKB-scale plan at
 # 200 k samples): method="auto" keeps to the one-kernel form unless this is switched on.
 LOCAL_AUTO = False
+# transform_host(result="auto"): results of this many bytes or more leave the device bit-packed and are widened
+# by the host copy engine; smaller ones as bytes (one DMA, no extra kernel, no hand-off to the pool)
+RESULT_BITS_MIN = 8 << 20
 
 
 def require_cuda() -> None:
@@ -345,27 +348,28 @@ class _Region:
         return strides, pitch * (n if self.sample_major else p)
 
 
-def _region(a: np.ndarray, s0: int, s1: int) -> _Region:
+def _region(a: np.ndarray, s0: int, s1: int, depth: int = 2) -> _Region:
+    """`depth`: strand indices covered (3 = with the phase byte, for the QC pass)."""
     n, p = s1 - s0, a.shape[1]
     ss, sv, sc = a.strides
     r = _Region()
     r.keep = None
     ok = ss > 0 and sv > 0 and sc > 0
     if ok and ss >= sv:
-        width = (p - 1) * sv + sc + 1
+        width = (p - 1) * sv + (depth - 1) * sc + 1
         ok = width <= ss or n <= 1
         sample_major = True
     elif ok:
-        width = (n - 1) * ss + sc + 1
+        width = (n - 1) * ss + (depth - 1) * sc + 1
         ok = width <= sv or p <= 1
         sample_major = False
     if not ok:
         # exotic views (negative or overlapping strides): one contiguous host copy
-        c = np.ascontiguousarray(a[s0:s1, :, :2])
+        c = np.ascontiguousarray(a[s0:s1, :, :depth])
         r.keep = c
         a, s0 = c, 0
         ss, sv, sc = c.strides
-        width, sample_major = (p - 1) * sv + sc + 1, True
+        width, sample_major = (p - 1) * sv + (depth - 1) * sc + 1, True
     r.ptr = a.ctypes.data + s0 * ss
     r.sample_major = sample_major
     r.ss, r.sv, r.sc = ss, sv, sc
@@ -409,13 +413,42 @@ def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
     return t.numpy()[:nbytes].view(dtype).reshape(shape)
 
 
-class _HostPipe:
-    """One device's share of transform_host: double-buffered H2D / compute / D2H on three streams."""
+def _submit(ticket: int, what: str) -> int:
+    if ticket < 0:
+        raise HaptoolsCudaError(f"{what}: {_cuda.lib().ht_last_error().decode('utf-8', 'replace')}")
+    return ticket
 
-    def __init__(self, dev, plan, dplan, gt, ancestry, bounds, chunk, pack_mode, out, H):
+
+def _host_wait(ticket) -> None:
+    if ticket:
+        check(_cuda.lib().ht_host_wait(ticket), "ht_host_wait")
+
+
+def _pageable(ptr: int, nbytes: int) -> bool:
+    """Ordinary host memory of a size worth the host copy engine (pool of threads + page-locked slots)?"""
+    return nbytes >= (4 << 20) and bool(_cuda.lib().ht_host_is_pageable(ptr))
+
+
+class _HostPipe:
+    """One device's share of transform_host: its chunks flow through upload -> kernels -> download, two of
+    everything, each stage asynchronous to the one Python thread that drives all devices.
+
+    upload    page-locked source: a pitched DMA (or the row-gather kernel) on the copy stream; PAGEABLE source:
+              a job of the host copy engine (ht_host_submit_upload), waited for just before the chunk's kernels
+    kernels   [re-layout] -> pack -> transform on the compute stream
+    download  result="bits" (default for results of 8 MB or more): ht_transform_bits -> ht_bits_to_rowbits, and
+              the host copy engine brings 1 bit per hap-call over PCIe and widens it into the caller's array
+              (ht_host_submit_download_expand) -- page-locked or not; result="u8": the bytes themselves, by
+              DMA into a page-locked array or through the engine's slots into a pageable one
+    """
+
+    def __init__(self, dev, plan, dplan, gt, ancestry, bounds, chunk, pack_mode, out, H, result):
         self.dev, self.plan, self.pack_mode, self.H = dev, plan, pack_mode, H
         self.gt, self.ancestry, self.out_ptr = gt, ancestry, out.ctypes.data
+        self.bounds = bounds
         self.p = gt.shape[1]
+        self.result = result
+        lib = _cuda.lib()
         with torch.cuda.device(dev):
             self.dplan = dplan if dplan is not None and dplan.device == dev else device_plan(plan, dev)
             self.nbuf = nbuf = min(2, len(bounds))
@@ -427,6 +460,11 @@ class _HostPipe:
             r0 = _region(gt, *bounds[0])
             self.gather = (not r0.sample_major and r0.keep is None and 0 < 2 * plan.n_vars <= self.p
                            and r0.width <= (8 << 20))
+            if self.gather and plan.has_ancestry:
+                # the row gather needs the ancestry array in the same (variant-major) layout; any other layout
+                # takes the full upload, like the reference accepts any layout
+                ra0 = _region(ancestry, *bounds[0])
+                self.gather = not (ra0.sample_major or ra0.keep is not None or ra0.width > (8 << 20))
             self.rows_idx = np.ascontiguousarray(plan.var_col, dtype=np.uint32) if self.gather else None
             self.pv = plan.n_vars if self.gather else self.p  # variant rows held by the device buffers
             self.tables = self.dplan.compact_tables() if self.gather else None
@@ -437,15 +475,19 @@ class _HostPipe:
             self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.anc_buf = [None] * nbuf
             if plan.has_ancestry:
-                ra0 = _region(ancestry, *bounds[0])
-                if self.gather and (ra0.sample_major or ra0.keep is not None or ra0.width > (8 << 20)):
-                    raise ValueError("ancestry must have the memory layout of the genotypes")
                 if self.gather:
                     anc_bytes = max(plan.n_vars * _region(ancestry, *b).dev_pitch() for b in ends)
                 else:
                     anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in ends)
                 self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-            self.out_buf = [torch.empty(chunk * self.pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            if result == "bits":
+                self.bits_pitch = int(lib.ht_rowbits_pitch(H))
+                tiles = (chunk + TILE - 1) // TILE
+                self.bits = torch.empty((tiles, H, 32, 2), dtype=torch.int32, device=dev)
+                self.out_buf = [torch.empty(chunk * self.bits_pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            else:
+                self.out_buf = [torch.empty(chunk * self.pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.out_pageable = _pageable(self.out_ptr, out.nbytes)
             self.planes = alloc_planes(chunk, plan.n_keys, dev)
             self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.cur = torch.cuda.current_stream(dev)
@@ -453,34 +495,76 @@ class _HostPipe:
                 st.wait_stream(self.cur)
         self.dense_gt = self.dense_anc = None  # scratch of the on-device re-layout (compute stream only)
         self.ev_h2d, self.ev_cmp, self.ev_d2h = [None] * nbuf, [None] * nbuf, [None] * nbuf
+        self.up_ticket = [[] for _ in range(nbuf)]  # host copy engine jobs of the chunk being uploaded into buffer b
+        self.dl_ticket = [0] * nbuf                 # ... and of the result leaving buffer b
+        self.regions = [None] * nbuf
         self.keep = []
         self.k = 0
-        self.pending = None  # (buffer, first sample, rows) of the chunk whose result has not been asked for yet
 
-    def submit(self, s0: int, s1: int) -> None:
-        """Queue chunk [s0, s1) on this device; returns at once (everything is asynchronous)."""
-        plan, dev, H, p = self.plan, self.dev, self.H, self.p
-        b = self.k % self.nbuf
+    def step(self) -> None:
+        """Queue this device's next chunk; everything is asynchronous except the waits for host copy engine
+        jobs whose buffers are needed again."""
+        k = self.k
         self.k += 1
-        rows = s1 - s0
-        s_in, s_cmp, s_out = self.s_in, self.s_cmp, self.s_out
-        with torch.cuda.device(dev):
-            # H2D (the previous user of this input buffer must have been packed)
+        if k == 0:
+            self._start_upload(0)
+        if k + 1 < len(self.bounds):
+            self._start_upload(k + 1)  # flies while chunk k's kernels are queued
+        self._compute(k)
+
+    def _start_upload(self, k: int) -> None:
+        b = k % self.nbuf
+        s0, s1 = self.bounds[k]
+        with torch.cuda.device(self.dev):
+            # the previous user of this input buffer must have been packed
             if self.ev_cmp[b] is not None:
-                s_in.wait_event(self.ev_cmp[b])
+                self.s_in.wait_event(self.ev_cmp[b])
             rg = _region(self.gt, s0, s1)
-            self.keep.append(rg.keep)
-            self._upload(self.gt_buf[b], rg, s_in)
-            ra = None
-            if plan.has_ancestry:
-                ra = _region(self.ancestry, s0, s1)
-                self.keep.append(ra.keep)
-                self._upload(self.anc_buf[b], ra, s_in)
-            self.ev_h2d[b] = s_in.record_event()
-            # compute (the previous result in this output buffer must have left)
+            ra = _region(self.ancestry, s0, s1) if self.plan.has_ancestry else None
+            self.keep += [rg.keep, ra.keep if ra else None]
+            self.up_ticket[b] = [self._upload(self.gt_buf[b], rg)]
+            if ra is not None:
+                self.up_ticket[b].append(self._upload(self.anc_buf[b], ra))
+            self.ev_h2d[b] = self.s_in.record_event()
+            self.regions[b] = (rg, ra)
+
+    def _upload(self, buf: torch.Tensor, reg: "_Region") -> int:
+        """Host region -> device buffer with 16-byte aligned rows; in gather mode only the referenced variants.
+        Returns the host copy engine's ticket (0: the copy is in stream order on s_in)."""
+        lib, st = _cuda.lib(), self.s_in.cuda_stream
+        pageable = _pageable(reg.ptr, reg.width * reg.rows) and reg.width <= (8 << 20)
+        if self.gather:
+            if pageable:
+                return _submit(lib.ht_host_submit_upload(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
+                                                         len(self.rows_idx), self.rows_idx.ctypes.data, st),
+                               "ht_host_submit_upload")
+            check(lib.ht_copy_rows_h2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
+                                       self.rows_idx.ctypes.data, len(self.rows_idx), st), "ht_copy_rows_h2d")
+            return 0
+        if pageable:
+            return _submit(lib.ht_host_submit_upload(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
+                                                     reg.rows, None, st), "ht_host_submit_upload")
+        _copy2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width, reg.rows, _cuda.HT_COPY_H2D, self.s_in)
+        return 0
+
+    def _compute(self, k: int) -> None:
+        plan, dev, H = self.plan, self.dev, self.H
+        b = k % self.nbuf
+        s0, s1 = self.bounds[k]
+        rows = s1 - s0
+        s_cmp = self.s_cmp
+        lib = _cuda.lib()
+        with torch.cuda.device(dev):
+            for t in self.up_ticket[b]:  # pageable source: its data is in device memory when the job is done
+                _host_wait(t)
+            self.up_ticket[b] = []
             s_cmp.wait_event(self.ev_h2d[b])
+            # the previous result in this output buffer must have left
+            _host_wait(self.dl_ticket[b])
+            self.dl_ticket[b] = 0
             if self.ev_d2h[b] is not None:
                 s_cmp.wait_event(self.ev_d2h[b])
+            rg, ra = self.regions[b]
             g_ptr, g_str = self.gt_buf[b].data_ptr(), rg.dev_strides()
             a_ptr, a_str = (_ptr(self.anc_buf[b]), ra.dev_strides()) if ra else (0, (0, 0, 0))
             if self.pack_mode == _cuda.HT_PACK_AUTO:
@@ -491,48 +575,43 @@ class _HostPipe:
                     if self.dense_gt is None or self.dense_gt.numel() < d_bytes:
                         with torch.cuda.stream(s_cmp):
                             self.dense_gt = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(g_ptr, *map(int, g_str), rows, self.pv, self.dense_gt.data_ptr(),
-                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    check(lib.ht_relayout_u8(g_ptr, *map(int, g_str), rows, self.pv, self.dense_gt.data_ptr(),
+                                             d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
                     g_ptr, g_str = self.dense_gt.data_ptr(), d_str
                 if ra and not _fast_layout(a_str):
                     d_str, d_bytes = ra.dense(rows, self.pv)
                     if self.dense_anc is None or self.dense_anc.numel() < d_bytes:
                         with torch.cuda.stream(s_cmp):
                             self.dense_anc = torch.empty(d_bytes, dtype=torch.uint8, device=dev)
-                    check(_cuda.lib().ht_relayout_u8(a_ptr, *map(int, a_str), rows, self.pv, self.dense_anc.data_ptr(),
-                                                    d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
+                    check(lib.ht_relayout_u8(a_ptr, *map(int, a_str), rows, self.pv, self.dense_anc.data_ptr(),
+                                             d_str[0], d_str[1], s_cmp.cuda_stream), "ht_relayout_u8")
                     a_ptr, a_str = self.dense_anc.data_ptr(), d_str
             pack(self.dplan, g_ptr, g_str, rows, self.planes, a_ptr, a_str, None, self.pack_mode, s_cmp, tables=self.tables)
+            dst = self.out_ptr + s0 * 2 * H
+            if self.result == "bits":
+                transform_bits(self.dplan, self.planes, rows, self.bits, s_cmp)
+                check(lib.ht_bits_to_rowbits(self.bits.data_ptr(), rows, H, self.out_buf[b].data_ptr(), self.bits_pitch,
+                                             s_cmp.cuda_stream), "ht_bits_to_rowbits")
+                self.ev_cmp[b] = s_cmp.record_event()
+                self.dl_ticket[b] = _submit(
+                    lib.ht_host_submit_download_expand(dst, 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.bits_pitch, rows,
+                                                       s_cmp.cuda_stream), "ht_host_submit_download_expand")
+                return
             transform_u8(self.dplan, self.planes, rows, self.out_buf[b].data_ptr(), self.pitch, s_cmp)
             self.ev_cmp[b] = s_cmp.record_event()
-            # D2H of the PREVIOUS chunk: asked for after this chunk's upload and kernels are queued, because the
-            # copy blocks the host when the result lies in pageable memory (ht_copy2d then moves it through
-            # its bounce buffers on a few host threads)
-            self._download()
-            self.pending = (b, s0, rows)
-
-    def _download(self) -> None:
-        if self.pending is None:
-            return
-        b, s0, rows = self.pending
-        self.pending = None
-        H = self.H
-        with torch.cuda.device(self.dev):
+            if self.out_pageable and 2 * H <= (8 << 20):
+                self.dl_ticket[b] = _submit(
+                    lib.ht_host_submit_download(dst, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows,
+                                                s_cmp.cuda_stream), "ht_host_submit_download")
+                return
             self.s_out.wait_event(self.ev_cmp[b])
-            _copy2d(self.out_ptr + s0 * 2 * H, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, self.s_out)
+            _copy2d(dst, 2 * H, self.out_buf[b].data_ptr(), self.pitch, 2 * H, rows, _cuda.HT_COPY_D2H, self.s_out)
             self.ev_d2h[b] = self.s_out.record_event()
 
-    def _upload(self, buf: torch.Tensor, reg: "_Region", stream) -> None:
-        """Host region -> device buffer with 16-byte aligned rows; in gather mode only the referenced variants."""
-        if self.gather:
-            check(_cuda.lib().ht_copy_rows_h2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
-                                               self.rows_idx.ctypes.data, len(self.rows_idx), stream.cuda_stream),
-                  "ht_copy_rows_h2d")
-        else:
-            _copy2d(buf.data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width, reg.rows, _cuda.HT_COPY_H2D, stream)
-
     def finish(self) -> None:
-        self._download()
+        for b in range(self.nbuf):
+            _host_wait(self.dl_ticket[b])
+            self.dl_ticket[b] = 0
         with torch.cuda.device(self.dev):
             self.s_out.synchronize()
             self.s_cmp.synchronize()
@@ -540,22 +619,33 @@ class _HostPipe:
             self.cur.wait_stream(self.s_out)
 
 
+def _gatherable(a: np.ndarray, plan: TransformPlan) -> bool:
+    """Variant-major host array (a variant is a contiguous row of at most 8 MB) of which the plan refers to at
+    most half the variants: only the referenced rows need to be uploaded."""
+    if a.shape[0] == 0:
+        return False
+    r = _region(a, 0, min(a.shape[0], TILE))
+    return not r.sample_major and r.keep is None and 0 < 2 * plan.n_vars <= a.shape[1] and \
+        ((a.shape[0] - 1) * r.ss + r.sc + 1) <= (8 << 20)
+
+
 def upload_bytes(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None) -> int:
     """Bytes transform_host copies to the device for these arrays: the bytes a[:, :, :2] spans, or -- for a
     variant-major array of which the plan refers to at most half the variants -- only the referenced rows."""
     total = 0
+    gather = _gatherable(gt, plan) and (ancestry is None or _gatherable(ancestry, plan))
     for a in (gt, ancestry):
         if a is None or a.shape[0] == 0:
             continue
         r = _region(a, 0, a.shape[0])
-        gather = not r.sample_major and r.keep is None and 0 < 2 * plan.n_vars <= a.shape[1] and r.width <= (8 << 20)
         total += r.width * (plan.n_vars if gather else r.rows)
     return int(total)
 
 
 def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,
                    chunk_samples: int = None, out: np.ndarray = None, pin_output: bool = None,
-                   dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO, devices=None) -> np.ndarray:
+                   dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO, devices=None,
+                   result: str = "auto") -> np.ndarray:
     """
     gt (n, p, 2|3) uint8/bool host array (a view is fine: VCF-style transposed, PGEN-style
     with a phase column, C-contiguous ...) -> (n, H, 2) numpy bool, bit-identical to the
@@ -564,6 +654,12 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
     devices  optional list of CUDA devices (or "all"): sample chunks are dealt round-robin to
              them -- samples shard with no communication, and every GPU brings its own PCIe
              link, which is what bounds this call.  Default: the one current (or `device`) GPU.
+    result   how the result leaves the device.  "bits": one BIT per hap-call crosses PCIe
+             (ht_transform_bits -> ht_bits_to_rowbits) and the host copy engine widens it to bool bytes
+             straight into the result array, page-locked or not (1/8 of the D2H bytes; the host's store
+             bandwidth becomes the bound); "u8": the bytes themselves (DMA into a page-locked array, through
+             the engine's slots into a pageable one); "auto": "bits" for results of RESULT_BITS_MIN bytes or
+             more (HAPTOOLS_B200_RESULT in the environment overrides).
     """
     require_cuda()
     if gt.ndim != 3 or gt.shape[2] < 2 or gt.dtype not in (np.uint8, np.bool_):
@@ -596,22 +692,141 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
         out = pinned_empty((n, H, 2)) if pin_output else np.empty((n, H, 2), dtype=np.uint8)
     elif out.shape != (n, H, 2) or out.dtype.itemsize != 1 or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous 1-byte array of shape (n, H, 2)")
-    result = out.view(np.bool_)
+    view = out.view(np.bool_)
     if n == 0 or H == 0:
-        return result
+        return view
     chunk = chunk_samples or default_chunk(n, p, H)
     if len(devs) > 1 and not chunk_samples:  # at least two chunks per device keep its three streams busy
         chunk = min(chunk, max(TILE, -(-n // (2 * len(devs))) // TILE * TILE))
     chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
     bounds = _ramped_bounds(n, chunk, len(devs)) if not chunk_samples else [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
     devs = devs[: len(bounds)]
-    pipes = [_HostPipe(d, plan, dplan, gt, ancestry, bounds[i :: len(devs)], chunk, pack_mode, out, H)
+    if result == "auto":
+        result = os.environ.get("HAPTOOLS_B200_RESULT", "").strip().lower() or "auto"
+    if result == "auto":
+        result = "bits" if out.nbytes >= RESULT_BITS_MIN and 2 * H <= (8 << 20) * 8 else "u8"
+    if result not in ("bits", "u8"):
+        raise ValueError("result must be 'auto', 'bits' or 'u8'")
+    pipes = [_HostPipe(d, plan, dplan, gt, ancestry, bounds[i :: len(devs)], chunk, pack_mode, out, H, result)
              for i, d in enumerate(devs)]
-    for k, (s0, s1) in enumerate(bounds):
-        pipes[k % len(pipes)].submit(s0, s1)
+    for k in range(len(bounds)):
+        pipes[k % len(pipes)].step()
     for pipe in pipes:
         pipe.finish()
-    return result
+    return view
+
+
+# --------------------------------------------------------------------------------------
+# QC: one device pass instead of the reference's host passes
+# --------------------------------------------------------------------------------------
+class QCResult:
+    """What Genotypes.check_missing / check_biallelic / check_phase / check_maf need to know about a genotype
+    matrix (haptools/data/genotypes.py:444-625), from ONE pass on the device (ht_qc_u8).  `first_*` are
+    `(sample index, variant index)` of the pair np.nonzero would list first, or None."""
+
+    __slots__ = ("n_samples", "n_variants", "first_missing", "first_multiallelic", "first_unphased", "n_missing",
+                 "n_multiallelic", "samp_missing", "var_multiallelic", "alt_counts")
+
+    def maf(self) -> np.ndarray:
+        """haptools/data/genotypes.py:599-602."""
+        ref_af = self.alt_counts / (2 * self.n_samples)
+        return np.array([ref_af, 1 - ref_af]).min(axis=0)
+
+
+_QC_NONE = 0xFFFFFFFFFFFFFFFF
+
+
+def _qc_tensors(n: int, p: int, dev):
+    summary = torch.zeros(5, dtype=torch.int64, device=dev)
+    summary[:3] = -1  # first_* = ~0
+    return (summary, torch.zeros(max(n, 1), dtype=torch.uint8, device=dev), torch.zeros(max(p, 1), dtype=torch.uint8, device=dev),
+            torch.zeros(max(p, 1), dtype=torch.int64, device=dev))
+
+
+def _qc_result(n: int, p: int, tensors) -> QCResult:
+    summary, samp, varm, alt = tensors
+    vals = summary.cpu().numpy().view(np.uint64)
+    r = QCResult()
+    r.n_samples, r.n_variants = n, p
+    pair = lambda k: None if int(k) == _QC_NONE else (int(k) >> 32, int(k) & 0xFFFFFFFF)  # noqa: E731
+    r.first_missing, r.first_multiallelic, r.first_unphased = pair(vals[0]), pair(vals[1]), pair(vals[2])
+    r.n_missing, r.n_multiallelic = int(vals[3]), int(vals[4])
+    r.samp_missing = samp[:n].cpu().numpy().astype(np.bool_)
+    r.var_multiallelic = varm[:p].cpu().numpy().astype(np.bool_)
+    r.alt_counts = alt[:p].cpu().numpy()
+    return r
+
+
+def qc_device(gt: torch.Tensor, missing_min: int = 254) -> QCResult:
+    """QC of a genotype tensor resident in HBM: (n, p, 2|3) uint8/bool, any strides."""
+    require_cuda()
+    _check_gt_tensor(gt, "gt")
+    n, p, depth = int(gt.shape[0]), int(gt.shape[1]), min(int(gt.shape[2]), 3)
+    with torch.cuda.device(gt.device):
+        tensors = _qc_tensors(n, p, gt.device)
+        check(_cuda.lib().ht_qc_u8(gt.data_ptr(), *map(int, gt.stride()), depth, n, p, 0, missing_min, tensors[0].data_ptr(),
+                                   tensors[1].data_ptr(), tensors[2].data_ptr(), tensors[3].data_ptr(), _stream_ptr()), "ht_qc_u8")
+        return _qc_result(n, p, tensors)
+
+
+def qc_host(data: np.ndarray, missing_min: int = 254, device=None, chunk_bytes: int = 256 << 20) -> QCResult:
+    """
+    QC of a host genotype matrix `(n, p, 2|3)` uint8/bool (any of the reference's layouts): sample chunks are
+    uploaded (DMA from page-locked memory, host copy engine from pageable memory) while the previous chunk is
+    checked by ht_qc_u8; the host never looks at a genotype byte.  Replaces the numpy passes of
+    Genotypes.check_missing / check_biallelic / check_phase / check_maf (haptools/data/genotypes.py:444-625).
+    """
+    require_cuda()
+    if data.ndim != 3 or data.shape[2] < 2 or data.dtype not in (np.uint8, np.bool_):
+        raise ValueError("genotypes must have shape (samples, variants, >=2) and dtype uint8 or bool")
+    n, p, depth = data.shape[0], data.shape[1], min(data.shape[2], 3)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = _cuda.lib()
+    with torch.cuda.device(dev):
+        tensors = _qc_tensors(n, p, dev)
+        if n == 0 or p == 0:
+            return _qc_result(n, p, tensors)
+        rows = max(1, min(n, chunk_bytes // max(1, depth * p)))
+        if rows < n:
+            rows = max(TILE, rows // TILE * TILE)
+        bounds = [(s, min(n, s + rows)) for s in range(0, n, rows)]
+        nbuf = min(2, len(bounds))
+        nbytes = max(_region(data, *b, depth=depth).dev_bytes() for b in bounds[:1] + bounds[-1:])
+        bufs = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        s_in, s_cmp, cur = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        s_in.wait_stream(cur)
+        s_cmp.wait_stream(cur)
+        ev_cmp, keep = [None] * nbuf, []
+
+        def upload(k):
+            b = k % nbuf
+            if ev_cmp[b] is not None:
+                s_in.wait_event(ev_cmp[b])
+            reg = _region(data, *bounds[k], depth=depth)
+            keep.append(reg.keep)
+            ticket = 0
+            if _pageable(reg.ptr, reg.width * reg.rows) and reg.width <= (8 << 20):
+                ticket = _submit(lib.ht_host_submit_upload(bufs[b].data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width,
+                                                           reg.rows, None, s_in.cuda_stream), "ht_host_submit_upload")
+            else:
+                _copy2d(bufs[b].data_ptr(), reg.dev_pitch(), reg.ptr, reg.pitch, reg.width, reg.rows, _cuda.HT_COPY_H2D, s_in)
+            return reg, ticket, s_in.record_event()
+
+        nxt = upload(0)
+        for k, (s0, s1) in enumerate(bounds):
+            reg, ticket, ev = nxt
+            if k + 1 < len(bounds):
+                nxt = upload(k + 1)
+            _host_wait(ticket)
+            s_cmp.wait_event(ev)
+            ss, sv, sc = reg.dev_strides()
+            check(lib.ht_qc_u8(bufs[k % nbuf].data_ptr(), ss, sv, sc, depth, s1 - s0, p, s0, missing_min, tensors[0].data_ptr(),
+                               tensors[1].data_ptr() + s0, tensors[2].data_ptr(), tensors[3].data_ptr(), s_cmp.cuda_stream),
+                  "ht_qc_u8")
+            ev_cmp[k % nbuf] = s_cmp.record_event()
+        s_cmp.synchronize()
+        cur.wait_stream(s_cmp)
+        return _qc_result(n, p, tensors)
 
 
 def transform_host_bits(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,

@@ -205,7 +205,7 @@ def _variant_columns(gts, var_ids: Sequence[str], who: str) -> list:
 
 
 def plan_from_haplotypes_loop(haps: Sequence, gts, ancestry: bool = False, who: str = None,
-                         unknown_label: str = "raise"):
+                         unknown_label: str = "raise", clip_bool: bool = True):
     """
     The literal, per-allele Python loop of the reference (kept as the cross-check of the
     vectorised plan_from_haplotypes below; tests/test_plan.py compares the two).
@@ -255,7 +255,7 @@ def plan_from_haplotypes_loop(haps: Sequence, gts, ancestry: bool = False, who: 
         except ValueError:
             raise ValueError("Some alleles were not present in the genotypes")
     allele_arr = np.asarray(allele_arr, dtype=np.int64).reshape(-1)
-    if as_bool:
+    if as_bool and clip_bool:
         # the reference builds allele_arr with dtype=bool (haplotypes.py:1398)
         allele_arr = np.minimum(allele_arr, 1)
     lens = np.fromiter((len(x) for x in idxs), dtype=np.int64, count=len(idxs))
@@ -296,7 +296,7 @@ def _allele_indices(var_alleles, cols: np.ndarray, allele_strs: list, ancestry: 
 
 
 def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str = None,
-                         unknown_label: str = "raise"):
+                         unknown_label: str = "raise", clip_bool: bool = True, log=None):
     """
     Same contract as plan_from_haplotypes_loop (the reference's host steps,
     haptools/data/haplotypes.py:1375-1401 / haptools/transform.py:103-135, exceptions
@@ -306,6 +306,14 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
     (column, allele[, label]) triples with one np.unique.  (De-duplicating by (column, allele
     index) instead of the reference's (ID, allele string) yields the same matrix: equal keys
     give equal planes.)
+
+    clip_bool  the PLURAL forms build ``allele_arr`` with ``dtype=gts.data.dtype`` (haplotypes.py:1398), so
+               with bool genotypes an allele index >= 2 becomes True and matches like 1; the SINGLE forms
+               (haplotypes.py:499-511) keep an integer array, and ``2 == True`` is False -- pass
+               ``clip_bool=False`` there (a key with allele >= 2 then never matches 0/1 bytes).
+    log        a logger that receives, at the step each belongs to, the two debug lines the reference emits
+               before its arithmetic (haplotypes.py:1387, 1389 / transform.py:122, 124), verbatim:
+               ``len(alleles)`` there counts distinct (variant ID, allele STRING) pairs.
     """
     H = len(haps)
     lens = np.fromiter((len(h.variants) for h in haps), dtype=np.int64, count=H)
@@ -327,6 +335,8 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
         ref_label = np.repeat(lab & 0xFF, lens)
     ids = [v.id for h in haps for v in h.variants]
     allele_strs = [v.allele for h in haps for v in h.variants]
+    if log is not None:
+        log.debug(f"Copying genotypes for {len(set(zip(ids, allele_strs)))} distinct alleles")
     gts.index(samples=False, variants=True)
     var_idx = gts._var_idx
     try:
@@ -337,8 +347,10 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
             f"Variants {set(missing)} are present in {who or 'the haplotypes'} but absent in the provided genotypes"
         )
     var_alleles = gts.variants["alleles"] if len(ids) else ()
+    if log is not None:
+        log.debug("Creating array denoting alt allele status")
     allele_idx = _allele_indices(var_alleles, cols, allele_strs, ancestry)
-    if gts.data.dtype == np.bool_:
+    if clip_bool and gts.data.dtype == np.bool_:
         # the reference builds allele_arr with dtype=bool (haplotypes.py:1398)
         allele_idx = np.minimum(allele_idx, 1)
     plan = plan_from_refs(cols, allele_idx, hap_off, gts.data.shape[1], ref_label)

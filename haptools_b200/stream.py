@@ -181,8 +181,9 @@ def pgen_write_batches(bits: torch.Tensor, n_samples: int, chunk_haps: int = 102
     (haptools/data/genotypes.py:1611-1642), produced from the transform's bit-packed result
     without ever building, transposing or widening the `(n, H, 2)` matrix on the host: yields
     `(start, end, subset_data, allele_cts)` with `subset_data` a C-contiguous `(end - start, 2 n)`
-    host array of `dtype` (page-locked, reused two yields later -- consume it before asking for
-    the one after next) and `allele_cts` = 2 for every row (a 0/1 matrix never has missing calls
+    host array of `dtype` (one of THREE page-locked buffers used in turn: batch k stays valid while
+    batch k + 1 is asked for and is overwritten when batch k + 2 is -- a writer thread may hold one
+    batch while the next is fetched) and `allele_cts` = 2 for every row (a 0/1 matrix never has missing calls
     and `_num_unique_alleles` floors at 2, genotypes.py:1538-1567).  The expansion of chunk
     k + 1 and its device->host copy overlap the consumer's work on chunk k.
     """
@@ -196,15 +197,17 @@ def pgen_write_batches(bits: torch.Tensor, n_samples: int, chunk_haps: int = 102
         s_cmp, cur = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
         s_cmp.wait_stream(cur)
         dbuf = [torch.empty((chunk_haps, pitch), dtype=tdt, device=dev) for _ in range(2)]
-        hbuf = [torch.empty((chunk_haps, pitch), dtype=tdt, pin_memory=True) for _ in range(2)]
-        events = [None, None]
+        # three host buffers: launch(k + 1) runs BEFORE batch k is yielded and writes asynchronously, so with
+        # two it would overwrite batch k - 1 while the consumer may still hold it
+        hbuf = [torch.empty((chunk_haps, pitch), dtype=tdt, pin_memory=True) for _ in range(3)]
+        events = [None, None, None]
 
         def launch(k):
             a, b = k * chunk_haps, min(H, (k + 1) * chunk_haps)
             with torch.cuda.stream(s_cmp):
                 hapmajor_from_bits(bits, n_samples, a, b, tdt, out=dbuf[k % 2], stream=s_cmp)
-                hbuf[k % 2][: b - a].copy_(dbuf[k % 2][: b - a], non_blocking=True)
-                events[k % 2] = s_cmp.record_event()
+                hbuf[k % 3][: b - a].copy_(dbuf[k % 2][: b - a], non_blocking=True)
+                events[k % 3] = s_cmp.record_event()
 
         n_chunks = -(-H // chunk_haps) if n_samples > 0 else 0
         if n_chunks:
@@ -212,9 +215,9 @@ def pgen_write_batches(bits: torch.Tensor, n_samples: int, chunk_haps: int = 102
         for k in range(n_chunks):
             if k + 1 < n_chunks:
                 launch(k + 1)
-            events[k % 2].synchronize()
+            events[k % 3].synchronize()
             a, b = k * chunk_haps, min(H, (k + 1) * chunk_haps)
-            host = hbuf[k % 2].numpy()[: b - a, : 2 * n_samples]
+            host = hbuf[k % 3].numpy()[: b - a, : 2 * n_samples]
             if pitch != 2 * n_samples:
                 host = np.ascontiguousarray(host)
             yield a, b, host, np.full(b - a, 2, dtype=np.uint32)

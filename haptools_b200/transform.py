@@ -66,6 +66,13 @@ class GenotypesAncestry(data.GenotypesVCF):
         self.ancestry_labels = {}
         self.popnum_ancestry = {}
 
+    _MISSING_MIN = 255  # this class treats only 255 as missing (haptools/transform.py:360)
+
+    def _discard_samples(self, samp_idx, level: str = "info"):
+        # haptools/transform.py:363-373: the ancestry rows go too, and the line is logged at INFO
+        self.ancestry = np.delete(self.ancestry, samp_idx, axis=0)
+        super()._discard_samples(samp_idx, level="info")
+
     def _copy_fields_to(self, other):
         super()._copy_fields_to(other)
         other.ancestry, other.ancestry_labels = self.ancestry, self.ancestry_labels

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define HT_ABI_VERSION 7
+#define HT_ABI_VERSION 8
 
 #define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
 #define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
@@ -344,18 +344,47 @@ int ht_bp_ancestry(const uint64_t* blk_key, const uint8_t* blk_pop, const uint32
                    void* stream);
 
 /*
+ * Genotype QC in one pass over the device copy of `gts.data` -- what the reference's checks derive with full
+ * numpy passes on the host before transform_haps calls the transform (haptools/transform.py:623-631):
+ *   Genotypes.check_missing   haptools/data/genotypes.py:444-485  (any strand >= 254; GenotypesAncestry,
+ *                             haptools/transform.py:353-383: == 255 -- `missing_min`)
+ *   Genotypes.check_biallelic genotypes.py:487-528  (any strand > 1)
+ *   Genotypes.check_phase     genotypes.py:530-557  ((bool(g0) ^ bool(g1)) & ~bool(phase); depth == 3 only)
+ *   Genotypes.check_maf       genotypes.py:559-625  (per-variant count of non-zero strand values)
+ * gt element (s, v, c) at gt + s*s_samp + v*s_var + c*s_strand, c < depth (2, or 3 with the phase byte).
+ *   summary           DEVICE struct; the caller initialises first_* to ~0 and the counters to 0; the kernel
+ *                     atomically folds this call in, so sample chunks can be checked one after the other
+ *                     (`sample_offset` = index of this chunk's first sample in the whole matrix).  first_* =
+ *                     minimum of (sample << 32 | variant) over the offending pairs = the pair np.nonzero lists
+ *                     first on the (n, p) mask, i.e. the one the reference's error messages name.
+ *   samp_missing[n]   optional, caller-zeroed: 1 for every sample of this chunk with a missing call
+ *                     (check_missing(discard_also=True) deletes exactly these)
+ *   var_multiallelic[p]  optional, caller-zeroed: 1 for every variant with a value > 1 in some sample
+ *   var_alt_count[p]  optional, caller-zeroed uint64: accumulated count of non-zero strand values
+ */
+typedef struct ht_qc_summary {
+    uint64_t first_missing;
+    uint64_t first_multiallelic;
+    uint64_t first_unphased;
+    uint64_t n_missing;       /* (sample, variant) pairs with a missing call       */
+    uint64_t n_multiallelic;  /* (sample, variant) pairs with a value > 1 (check_biallelic's log line counts pairs) */
+} ht_qc_summary;
+
+int ht_qc_u8(const uint8_t* gt, int64_t s_samp, int64_t s_var, int64_t s_strand, int depth,
+             int64_t n_samples, int64_t n_vars, int64_t sample_offset, int missing_min,
+             ht_qc_summary* summary, uint8_t* samp_missing, uint8_t* var_multiallelic,
+             uint64_t* var_alt_count, void* stream);
+
+/*
  * Host <-> device plumbing for the Python host layer (GenotypesPLINK-style chunked input,
  * haptools/data/genotypes.py:1353-1406, and strided result read-back): a pitched 2-D copy
  * (cudaMemcpy2DAsync; `kind` = HT_COPY_*) and page-locking of an existing host range, so that
  * numpy buffers can be DMA'd without a staging copy.  h_ptr is a HOST pointer.
  * Dense buffers (both pitches == width) go out as one linear copy.  An HT_COPY_H2D source of 4 MB
  * or more in PAGEABLE host memory (what `gts.data` is when it comes from cyvcf2 / pgenlib / numpy)
- * is uploaded through the library's own page-locked bounce buffers by a few host threads
- * (HT_HOST_COPY_THREADS in the environment, default 4): 20 GB/s instead of the 11 GB/s of the
- * driver's single-threaded staging; the call returns when the source has been read.  An HT_COPY_D2H
- * destination of 4 MB or more in pageable memory is filled the same way in the other direction (the DMA
- * of a block into one bounce buffer flies while the previous block is copied out of the other one): 30
- * GB/s instead of 17.6; that call returns when the destination holds the data.
+ * is uploaded by the host copy engine below (submit + wait: the call returns when the data is in device
+ * memory) instead of the driver's single-threaded staging; an HT_COPY_D2H destination of 4 MB or more in
+ * pageable memory is filled the same way in the other direction (returns when the destination holds the data).
  */
 int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
               int64_t width_bytes, int64_t height, int kind, void* stream);
@@ -367,15 +396,62 @@ int ht_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
  * (1000G-scale config: 0.52 GB instead of 5 GB).  A PAGE-LOCKED source with 16-byte aligned rows (and dst) is
  * gathered by a kernel whose warps read the rows straight out of host memory over PCIe: asynchronous on
  * `stream`, no host thread touches a byte, the source must stay valid until the stream gets there (the
- * indices are copied during the call).  Any other source: host threads gather the rows into the page-locked
- * bounce buffers of ht_copy2d, every block leaves with an asynchronous DMA, the call returns when the source
- * has been read, and rows must fit a bounce buffer (8 MB).  HT_GATHER=bounce in the environment forces the
+ * indices are copied during the call).  Any other source: the host copy engine gathers the rows into its
+ * page-locked slots (submit + wait: the call returns when the rows are in device memory); rows must fit a
+ * slot (8 MB).  HT_GATHER=bounce in the environment forces the
  * second way (measurements, tests).
  */
 int ht_copy_rows_h2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
                      const uint32_t* row_idx, int64_t n_rows, void* stream);
 int ht_host_register(void* h_ptr, size_t bytes);
 int ht_host_unregister(void* h_ptr);
+
+/*
+ * The result as one bit string per sample: rowbits + s * pitch holds, at bit j % 8 of byte j / 8, result byte
+ * j = 2 h + c of sample s -- the bytes of the reference's `hap_gts.data[s]` (haplotypes.py:1408-1412) at one
+ * bit each.  This is the form in which a result leaves the device for a HOST array: 1/8 of the bytes cross
+ * PCIe, and the host only widens bits to bool bytes (ht_host_submit_download_expand).  `bits` is the packed
+ * result of ht_transform_bits; pitch >= ht_rowbits_pitch(n_haps) (= 4 * ceil(H / 16) rounded up to 16), a
+ * multiple of 4; bits of haplotypes >= n_haps are 0; rows >= n_samples are not touched.
+ */
+int64_t ht_rowbits_pitch(int64_t n_haps);
+int ht_bits_to_rowbits(const uint32_t* bits, int64_t n_samples, int64_t n_haps, uint8_t* rowbits,
+                       int64_t pitch, void* stream);
+
+/*
+ * Host copy engine (csrc/ht_hostcopy.cu): a persistent pool of host threads (HT_HOST_COPY_THREADS in the
+ * environment, default min(cores, 12)), each with two page-locked 8 MB staging slots and its own copy
+ * stream per device.  It serves the transfers that plain DMA cannot do well: PAGEABLE host memory on either
+ * side (what `gts.data` and the np.empty result are in the reference's API), the gather of selected rows,
+ * and the widening of the bit-packed result.  A job is asynchronous to the caller:
+ *   ht_host_submit_*  records an event on `stream` (the job starts when everything queued there so far has
+ *                     finished), queues the job and returns a ticket > 0 at once (-1: error, see
+ *                     ht_last_error).  The host buffers must stay valid until the ticket has been waited for.
+ *   ht_host_wait      returns when the job is complete: a download's destination holds the data, an
+ *                     upload's data is in device memory and visible to every stream.  ticket 0 = all jobs
+ *                     submitted so far.  Every ticket must be waited for once (its bookkeeping is freed then).
+ * Jobs of different devices and threads share the pool; workers prefer jobs whose event has fired.
+ *   upload            dst (device, pitched) <- h_src rows (h_row_idx != NULL: row r = source row h_row_idx[r];
+ *                     the indices are copied during the call); rows must fit a slot (8 MB)
+ *   download          h_dst (host, pitched) <- src (device)
+ *   download_expand   h_out row r (n_out_bytes bytes of 0x00 / 0x01) <- bit string r of `rowbits` (device,
+ *                     ht_bits_to_rowbits layout): the last step of Haplotypes.transform for a host result
+ * ht_expand_rowbits_host is the widening alone, on the calling thread, for bit strings already in host memory;
+ * ht_host_expand_isa(-1) tells which form runs (0 portable, 1 AVX2, 2 AVX-512BW); a value >= 0 caps it, -2
+ * lifts the cap (tests).
+ */
+int64_t ht_host_submit_upload(void* dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch,
+                              int64_t width_bytes, int64_t height, const uint32_t* h_row_idx, void* stream);
+int64_t ht_host_submit_download(void* h_dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                                int64_t width_bytes, int64_t height, void* stream);
+int64_t ht_host_submit_download_expand(void* h_out, int64_t out_pitch, int64_t n_out_bytes,
+                                       const void* rowbits, int64_t bits_pitch, int64_t n_rows, void* stream);
+int ht_host_wait(int64_t ticket);
+int ht_host_workers(void);
+int ht_host_is_pageable(const void* h_ptr); /* 1: ordinary (unregistered) host memory, 0: page-locked / device */
+int ht_expand_rowbits_host(const uint8_t* h_rowbits, int64_t bits_pitch, int64_t n_rows,
+                           int64_t n_out_bytes, uint8_t* h_out, int64_t out_pitch);
+int ht_host_expand_isa(int force);
 
 #ifdef __cplusplus
 }

@@ -72,3 +72,29 @@ def test_transform_to_pgen_batches_end_to_end():
     bits = engine.transform_device(torch.from_numpy(gt).cuda(), dplan, fmt="bits")
     rows = [sub.copy() for _, _, sub, _ in stream.pgen_write_batches(bits, n, chunk_haps=64)]
     np.testing.assert_array_equal(np.concatenate(rows), pwo.pgen_batch(want_mat, 0, H)[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [64, 1026])  # 2n % 4 == 0: the yield is a VIEW of the page-locked buffer
+def test_batch_stays_valid_while_the_next_one_is_fetched(n):
+    """The documented contract of pgen_write_batches: a consumer (e.g. a writer thread) may hold batch
+    k while it asks for batch k + 1; only batch k + 2 reuses k's buffer."""
+    import torch
+
+    from haptools_b200 import dist as hdist
+    from haptools_b200 import stream
+
+    H = 45
+    rng = np.random.default_rng(n)
+    result = rng.random((n, H, 2)) < 0.5
+    bits = torch.from_numpy(hdist.pack_result_bits(result).view(np.int32)).cuda()
+    want, _ = pwo.pgen_batch(result, 0, H)
+    gen = stream.pgen_write_batches(bits, n, chunk_haps=4)
+    held = next(gen)
+    for nxt in gen:
+        torch.cuda.synchronize()  # whatever the generator launched for later batches has landed
+        a, b, sub, _ = held
+        np.testing.assert_array_equal(sub, want[a:b])  # batch k, inspected AFTER batch k + 1 was produced
+        held = nxt
+    a, b, sub, _ = held
+    np.testing.assert_array_equal(sub, want[a:b])
