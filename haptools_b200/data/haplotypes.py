@@ -20,15 +20,6 @@ import numpy as np
 from .genotypes import GenotypesVCF
 
 
-def _reject_empty(hap, genotypes):
-    """The reference's single-haplotype form cannot broadcast its (1, 0) allele array against
-    (n, 0, 2) and raises (haptools/data/haplotypes.py:499-511); only the plural form maps a
-    haplotype without variants to all-True."""
-    if len(hap.variants) == 0:
-        n = genotypes.data.shape[0]
-        raise ValueError(f"operands could not be broadcast together with shapes (1,0) ({n},0,2) ")
-
-
 @dataclass
 class Variant:
     start: int
@@ -78,14 +69,9 @@ class Haplotype:
         Presence of this haplotype on each chromosome copy of each sample: ``(n, 2)`` bool.
         Replaces haptools/data/haplotypes.py:463-511.
         """
-        from .. import engine
-        from ..plan import plan_from_haplotypes
+        from ..integrate import haplotype_transform
 
-        # clip_bool=False: this form compares an INTEGER allele array (haplotypes.py:499-511), so with bool
-        # genotypes an allele index >= 2 never matches (the plural form's dtype=bool cast does not apply)
-        plan = plan_from_haplotypes([self], genotypes, ancestry=False, who=f"haplotype '{self.id}'", clip_bool=False)
-        _reject_empty(self, genotypes)
-        return engine.transform_host(genotypes.data, plan)[:, 0]
+        return haplotype_transform(self, genotypes)
 
 
 class Haplotypes:
@@ -116,39 +102,9 @@ class Haplotypes:
 
     # shared by the ancestry-aware subclass (haptools_b200/transform.py)
     def _transform(self, gts, hap_gts, ancestry: bool):
-        from .. import engine
-        from ..plan import plan_from_haplotypes
+        from ..integrate import haplotypes_transform
 
-        self.index()
-        haps = [self.data[hap] for hap in self.type_ids["H"]]
-        if hap_gts is None:
-            hap_gts = GenotypesVCF(fname=None, log=self.log)
-        hap_gts.samples = gts.samples
-        # haptools/data/haplotypes.py:1369-1372, column by column instead of a tuple per haplotype
-        variants = np.empty(len(haps), dtype=hap_gts.variants.dtype)
-        variants["id"] = [hap.id for hap in haps]
-        variants["chrom"] = [hap.chrom for hap in haps]
-        variants["pos"] = [hap.start for hap in haps]
-        variants["alleles"].fill(("A", "T"))
-        hap_gts.variants = variants
-        # the five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order (the first
-        # two are emitted by the planner at the steps they belong to)
-        plan = plan_from_haplotypes(haps, gts, ancestry=ancestry, log=self.log)
-        self.log.info(f"Transforming genotypes for {len(haps)} haplotypes")
-        self.log.debug(
-            f"Allocating array with dtype {gts.data.dtype} and size "
-            f"{(len(gts.samples), len(haps), 2)}"
-        )
-        self.log.debug("Computing haplotype genotypes. This may take a while")
-        if ancestry and gts.data.shape[2] != 2:
-            # haptools/transform.py:137 compares the whole last axis; a leftover phase column
-            # makes the reference fail with a broadcast error -- same exception class here
-            raise ValueError(
-                f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
-                f"into shape {(gts.data.shape[0], 2)}"
-            )
-        hap_gts.data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
-        return hap_gts
+        return haplotypes_transform(self, gts, hap_gts, ancestry, GenotypesVCF)
 
     def transform(self, gts: GenotypesVCF, hap_gts: GenotypesVCF = None) -> GenotypesVCF:
         """

@@ -28,21 +28,9 @@ class HaplotypeAncestry(data.Haplotype):
 
     def transform(self, genotypes) -> np.ndarray:
         """Replaces haptools/transform.py:31-68; returns ``(n, 2)`` bool."""
-        from . import engine
-        from .plan import plan_from_haplotypes
+        from .integrate import haplotype_ancestry_transform
 
-        plan, never = plan_from_haplotypes(
-            [self], genotypes, ancestry=True, who=f"haplotype '{self.id}'", unknown_label="never"
-        )
-        data.haplotypes._reject_empty(self, genotypes)
-        n, depth = genotypes.data.shape[0], genotypes.data.shape[2]
-        if depth != 2:
-            # haptools/transform.py:61 compares the whole last axis, so a leftover phase
-            # column makes the reference's logical_and fail to broadcast
-            raise ValueError(f"operands could not be broadcast together with shapes ({n},{depth}) ({n},2) ")
-        if never[0]:
-            return np.zeros((n, 2), dtype=np.bool_)
-        return engine.transform_host(genotypes.data, plan, ancestry=genotypes.ancestry)[:, 0]
+        return haplotype_ancestry_transform(self, genotypes)
 
 
 class HaplotypesAncestry(data.Haplotypes):

@@ -65,7 +65,7 @@ def load_case(path) -> dict:
 
 def list_golden() -> list[Path]:
     """Transform fixtures (the bp_*.npz breakpoint fixtures have their own loader)."""
-    return sorted(p for p in GOLDEN_DIR.glob("*.npz") if not p.name.startswith(("bp_", "pgenwrite_")))
+    return sorted(p for p in GOLDEN_DIR.glob("*.npz") if not p.name.startswith(("bp_", "pgenwrite_", "qc_")))
 
 
 def list_golden_bp() -> list[Path]:
