@@ -78,17 +78,11 @@ def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
     if hap_gts is None:
         hap_gts = genotypes_vcf(fname=None, log=haps_obj.log)
     hap_gts.samples = gts.samples
-    # haptools/data/haplotypes.py:1369-1372, column by column instead of a tuple per haplotype
-    variants = np.empty(len(haps), dtype=hap_gts.variants.dtype)
-    variants["id"] = [hap.id for hap in haps]
-    variants["chrom"] = [hap.chrom for hap in haps]
-    variants["pos"] = [hap.start for hap in haps]
-    variants["alleles"].fill(("A", "T"))
-    hap_gts.variants = variants
+    hap_gts.variants = _result_variants(haps_obj, haps, hap_gts.variants.dtype)
     # the five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order (the first
     # two are emitted by the planner at the steps they belong to)
     log = haps_obj.log
-    plan = plan_from_haplotypes(haps, gts, ancestry=ancestry, log=log)
+    plan = _cached_plan(haps_obj, haps, gts, ancestry, log)
     log.info(f"Transforming genotypes for {len(haps)} haplotypes")
     log.debug(
         f"Allocating array with dtype {gts.data.dtype} and size "
@@ -104,6 +98,86 @@ def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
         )
     hap_gts.data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
     return hap_gts
+
+
+# ----------------------------------------------------------------------------------------
+# plan cache
+# ----------------------------------------------------------------------------------------
+# The planner walks every Variant object of every haplotype (the reference's own O(K) dict loop,
+# haplotypes.py:1375-1386): 0.5 s for 100 k haplotypes / 1.1 M alleles, against 40 ms for transforming 16 k
+# samples.  Callers that transform several genotype sets (or sample batches) with the SAME haplotype set -- what
+# `haptools transform` on chunked input and `haptools ld` do -- get the plan of the previous call back when
+# nothing it was built from has been replaced: the `data` dict and `type_ids` of the Haplotypes object, the
+# `variants` TUPLE of every haplotype (tuples are immutable; the check is by identity, O(H)), the `variants`
+# array and ID index of the genotypes, the dtype class of `data` and the ancestry label dict.  What the check
+# cannot see is an IN-PLACE edit of a Variant's fields or of the genotypes' `variants` array between two calls;
+# code that does that sets HAPTOOLS_B200_PLAN_CACHE=0 (or calls clear_plan_cache(haps)).
+_CACHE_ATTR = "_haptools_b200_plan_cache"
+
+
+def clear_plan_cache(haps_obj) -> None:
+    haps_obj.__dict__.pop(_CACHE_ATTR, None)
+    haps_obj.__dict__.pop(_CACHE_ATTR + "_variants", None)
+
+
+def _result_variants(haps_obj, haps, dtype):
+    """``hap_gts.variants`` (haptools/data/haplotypes.py:1369-1372), built column by column instead of a tuple
+    per haplotype.  The string -> U50 conversions of the previous call are kept (as plain column arrays) and
+    reused when the (id, chrom, start) of every haplotype are what they were; the result is a fresh array
+    every time, like the reference's."""
+    fields = ([hap.id for hap in haps], [hap.chrom for hap in haps], [hap.start for hap in haps])
+    entry = haps_obj.__dict__.get(_CACHE_ATTR + "_variants")
+    if entry is None or entry[0] != fields or entry[1] != dtype:
+        cols = (np.asarray(fields[0], dtype=dtype["id"]), np.asarray(fields[1], dtype=dtype["chrom"]),
+                np.asarray(fields[2], dtype=dtype["pos"])) if len(haps) else None
+        entry = (fields, dtype, cols)
+        if _cache_enabled():
+            haps_obj.__dict__[_CACHE_ATTR + "_variants"] = entry
+    variants = np.empty(len(haps), dtype=dtype)
+    if len(haps):
+        variants["id"], variants["chrom"], variants["pos"] = entry[2]
+        variants["alleles"].fill(("A", "T"))
+    return variants
+
+
+def _cache_enabled() -> bool:
+    import os
+
+    return os.environ.get("HAPTOOLS_B200_PLAN_CACHE", "1").strip() not in ("0", "off", "no")
+
+
+def _cached_plan(haps_obj, haps, gts, ancestry, log):
+    from operator import is_
+
+    from .plan import plan_from_haplotypes
+
+    if not _cache_enabled():
+        return plan_from_haplotypes(haps, gts, ancestry=ancestry, log=log)
+    gts.index(samples=False, variants=True)  # raises on duplicate IDs like the planner would
+    tuples = [h.variants for h in haps]
+    stamp = (
+        haps_obj.data, gts.variants, gts._var_idx, gts.data.dtype == np.bool_, gts.data.shape[1], bool(ancestry),
+        tuple(sorted(gts.ancestry_labels.items())) if ancestry else None,
+        [h.ancestry for h in haps] if ancestry else None,
+    )
+    entry = haps_obj.__dict__.get(_CACHE_ATTR)
+    if entry is not None:
+        old_stamp, old_tuples, plan, n_distinct = entry
+        same = (
+            old_stamp[0] is stamp[0] and old_stamp[1] is stamp[1] and old_stamp[2] is stamp[2]
+            and old_stamp[3:] == stamp[3:] and len(old_tuples) == len(tuples)
+            and all(map(is_, old_tuples, tuples))
+        )
+        if same:
+            # the planner's two debug lines (haplotypes.py:1387, 1389), as on the first call
+            log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
+            log.debug("Creating array denoting alt allele status")
+            return plan
+    seen = []
+    plan = plan_from_haplotypes(haps, gts, ancestry=ancestry, log=log, n_distinct_out=seen)
+    # the entry keeps the tuples (and the two arrays) alive, so an `is` match can never be a recycled address
+    haps_obj.__dict__[_CACHE_ATTR] = (stamp, tuples, plan, seen[0])
+    return plan
 
 
 # ----------------------------------------------------------------------------------------

@@ -296,7 +296,7 @@ def _allele_indices(var_alleles, cols: np.ndarray, allele_strs: list, ancestry: 
 
 
 def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str = None,
-                         unknown_label: str = "raise", clip_bool: bool = True, log=None):
+                         unknown_label: str = "raise", clip_bool: bool = True, log=None, n_distinct_out: list = None):
     """
     Same contract as plan_from_haplotypes_loop (the reference's host steps,
     haptools/data/haplotypes.py:1375-1401 / haptools/transform.py:103-135, exceptions
@@ -335,8 +335,12 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
         ref_label = np.repeat(lab & 0xFF, lens)
     ids = [v.id for h in haps for v in h.variants]
     allele_strs = [v.allele for h in haps for v in h.variants]
-    if log is not None:
-        log.debug(f"Copying genotypes for {len(set(zip(ids, allele_strs)))} distinct alleles")
+    if log is not None or n_distinct_out is not None:
+        n_distinct = len(set(zip(ids, allele_strs)))  # the reference's len(alleles), haplotypes.py:1387
+        if n_distinct_out is not None:
+            n_distinct_out.append(n_distinct)
+        if log is not None:
+            log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
     gts.index(samples=False, variants=True)
     var_idx = gts._var_idx
     try:

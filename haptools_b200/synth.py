@@ -119,3 +119,42 @@ def synth_plan(p: int, n_haps: int, seed: int, n_pops: int = 0, **kw) -> Transfo
 def plan_to_csr(plan: TransformPlan):
     """(key_col, key_allele, hap_off, hap_key[, key_label]) for oracle.transform_from_csr."""
     return plan.key_col().astype(np.int64), plan.key_allele, plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64)
+
+
+def synth_objects(p: int, n_haps: int, seed: int, n_pops: int = 0, sort: bool = False, gts=None):
+    """
+    The same synthetic haplotype set as synth_plan, as the OBJECTS the class API takes (variant
+    IDs ``v{i}``, chrom "1", pos i + 1, alleles ("A", "C")): returns ``(haplotypes, gts)`` -- a
+    ``Haplotypes`` / ``HaplotypesAncestry`` holding ``n_haps`` ``Haplotype`` objects (population ``P{k}`` with
+    ``n_pops``), and a ``GenotypesVCF`` / ``GenotypesAncestry`` whose ``variants`` are filled in (``data``,
+    ``samples`` and ``ancestry`` are the caller's to set).  ``plan_from_haplotypes(haps, gts)`` on them gives the
+    tables of ``synth_plan(p, n_haps, seed, n_pops, sort=sort)``.
+    """
+    from . import data as hdata
+    from . import transform as htransform
+
+    ref_col, ref_allele, hap_off, hap_label = synth_haplotype_refs(p, n_haps, seed, n_pops=n_pops, sort=sort)
+    ids = np.char.add("v", np.arange(p).astype("U"))
+    if gts is None:
+        gts = (htransform.GenotypesAncestry if n_pops else hdata.GenotypesVCF)(fname=None)
+        variants = np.empty(p, dtype=gts.variants.dtype)
+        variants["id"], variants["chrom"], variants["pos"] = ids, "1", np.arange(1, p + 1)
+        variants["alleles"].fill(("A", "C"))
+        gts.variants = variants
+        if n_pops:
+            gts.ancestry_labels = {f"P{k}": k for k in range(n_pops)}
+    id_list = ids.tolist()
+    cols, alleles, off = ref_col.tolist(), ref_allele.tolist(), hap_off.tolist()
+    data = {}
+    for h in range(n_haps):
+        a, b = off[h], off[h + 1]
+        start, end = (cols[a] + 1, cols[b - 1] + 2) if b > a else (1, 2)
+        if n_pops:
+            hap = htransform.HaplotypeAncestry("1", start, end, f"H{h}", f"P{int(hap_label[h])}")
+        else:
+            hap = hdata.Haplotype("1", start, end, f"H{h}")
+        hap.variants = tuple(hdata.Variant(cols[j] + 1, cols[j] + 2, id_list[cols[j]], "C" if alleles[j] else "A") for j in range(a, b))
+        data[hap.id] = hap
+    haps = (htransform.HaplotypesAncestry if n_pops else hdata.Haplotypes)(fname=None)
+    haps.data = data
+    return haps, gts
