@@ -55,6 +55,7 @@ SIGNATURES = {
     "ht_pack_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p]),
     "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p]),
+    "ht_transform_u8_staged": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
     "ht_transform_bits_local": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "ht_unpack_bits_u8": (_i32, [_p, _i64, _i64, _p, _i64, _p]),

@@ -46,17 +46,19 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile and link the shared library; returns its path."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: list = None, out: Path = None) -> Path:
+    """Compile and link the shared library; returns its path.  `defines` / `out`: an experimental variant
+    (e.g. ["HT_STAGE_MIN_CTAS=2"]) written next to the product library and loaded through HT_LIB_PATH."""
+    lib_path = Path(out) if out else LIB_PATH
+    if not force and not defines and not out and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    objdir = REPO / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = REPO / "build" / (lib_path.stem if out else "")
+    objdir.mkdir(parents=True, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = objdir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in (defines or [])], f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -68,14 +70,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out:
             print(out, file=sys.stderr)
         objs.append(str(obj))
-    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+    tmp = lib_path.with_suffix(".so.tmp%d" % os.getpid())
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs, "--cudart", "static"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs or None, out=outs[0] if outs else None))

@@ -389,7 +389,7 @@ bits_to_rowbits_kernel(const uint32_t* __restrict__ bits, int64_t n_samples, int
         }
         transpose32(a);  // a[b] = the 32 result bits (16 haplotypes x 2 strands) of sample s0 + b
         const int rows = (int)min((int64_t)32, n_samples - s0);
-        uint8_t* p = rowbits + s0 * pitch + 64 * hb + 4 * lane;
+        uint8_t* p = rowbits + s0 * pitch + 128 * hb + 4 * lane;
 #pragma unroll
         for (int b = 0; b < 32; ++b)
             if (b < rows) *reinterpret_cast<uint32_t*>(p + (int64_t)b * pitch) = a[b];

@@ -445,10 +445,11 @@ static int check_common(const uint32_t* planes, int64_t n_samples, int64_t n_key
 
 extern "C" {
 
-int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
-                    const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
-                    const uint32_t* quads, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
-                    uint64_t* counts, void* stream) {
+static int transform_u8_impl(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                             const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                             const uint32_t* quads, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                             uint64_t* counts, void* stream, const uint32_t* blk_key_lo,
+                             const uint32_t* blk_key_cnt, int64_t stage_lines) {
     using namespace ht;
     if (int rc = check_common(planes, n_samples, n_keys, hap_off, hap_key, n_haps)) return rc;
     if (counts && n_haps > 0)
@@ -474,7 +475,7 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                     : ((addr | (uintptr_t)out_s_samp) & 1) == 0 ? 2 : 1;
     if (quads4 && vec == 16 && transform_half_enabled())
         return launch_transform_u8_half(planes, n_samples, n_keys, quad_off16, quads4, n_haps, out, out_s_samp, cnt,
-                                        (cudaStream_t)stream);
+                                        (cudaStream_t)stream, blk_key_lo, blk_key_cnt, stage_lines);
     // a grid holds at most 2^31-1 blocks: launch ranges of tile groups
     const int64_t groups_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
     const int64_t tiles_per_launch = groups_per_launch * kTilesPerCta;
@@ -494,6 +495,25 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
         HT_CUDA_TRY(cudaGetLastError());
     }
     return HT_OK;
+}
+
+int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                    const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                    const uint32_t* quads, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                    uint64_t* counts, void* stream) {
+    return transform_u8_impl(planes, n_samples, n_keys, hap_off, hap_key, quad_off16, quads, n_haps, out, out_s_samp,
+                             counts, stream, nullptr, nullptr, 0);
+}
+
+int ht_transform_u8_staged(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                           const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                           const uint32_t* quads, const uint32_t* blk_key_lo, const uint32_t* blk_key_cnt,
+                           int64_t stage_lines, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                           uint64_t* counts, void* stream) {
+    if (stage_lines < 0 || stage_lines > HT_STAGE_LINES_MAX) return ht::bad_arg("stage_lines out of range (0..HT_STAGE_LINES_MAX)");
+    if (stage_lines > 0 && (!blk_key_lo || !blk_key_cnt)) return ht::bad_arg("blk_key_lo / blk_key_cnt are NULL");
+    return transform_u8_impl(planes, n_samples, n_keys, hap_off, hap_key, quad_off16, quads, n_haps, out, out_s_samp,
+                             counts, stream, blk_key_lo, blk_key_cnt, stage_lines);
 }
 
 int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,

@@ -66,9 +66,12 @@ __device__ __forceinline__ void transpose32_dev(uint32_t (&a)[32]) {
 
 // half-tile form of the transform (ht_transform_half.cu); needs the planner's quads and 16-byte rows
 bool transform_half_enabled();
+// blk_key_lo / blk_key_cnt / stage_lines: optional key runs of the 128-haplotype blocks (staged form)
 int launch_transform_u8_half(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                              const uint32_t* quad_off16, const uint4* quads, int64_t n_haps, uint8_t* out,
-                             int64_t out_s_samp, unsigned long long* counts, cudaStream_t st);
+                             int64_t out_s_samp, unsigned long long* counts, cudaStream_t st,
+                             const uint32_t* blk_key_lo = nullptr, const uint32_t* blk_key_cnt = nullptr,
+                             int64_t stage_lines = 0);
 
 __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     uint4 o;

@@ -44,6 +44,9 @@ constexpr uint32_t kHQuadLast = 1u, kHQuadSkip = 2u, kHOffMask = 0xffffff00u;
 #ifndef HT_HALF_MIN_CTAS
 #define HT_HALF_MIN_CTAS 4
 #endif
+#ifndef HT_STAGE_MIN_CTAS
+#define HT_STAGE_MIN_CTAS 3
+#endif
 constexpr int kHBQ = HT_HALF_BQ;  // quads per batch: 2 * kHBQ loads (of 2 x 128 B) in flight per batch
 
 __device__ __forceinline__ uint2 ld_line(const char* lane_base, uint32_t off, uint64_t pol) {
@@ -56,6 +59,14 @@ __device__ __forceinline__ uint2 ld_line(const char* lane_base, uint32_t off, ui
     asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(off), "l"(lane_base));
     uint2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(addr), "l"(pol));
+    return v;
+}
+
+// staged form: the line sits in shared memory at the (transformed) offset; `lane_base` is then a shared-window
+// address (stage buffer + 8 * word)
+__device__ __forceinline__ uint2 ld_line_smem(uint32_t lane_base_s, uint32_t off) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(lane_base_s + off));
     return v;
 }
 
@@ -81,16 +92,22 @@ __device__ __forceinline__ void hemit(uint32_t flags, uint32_t& r0, uint32_t& r1
 // Staged form: `qp` points at the lane's pair (entries 0-1 or 2-3, flags replicated into entry 2) of
 // the warp's first quad in shared memory; the warp's stream was padded to a multiple of kHBQ quads
 // (copies of its last quad without flags), so there is no clamping and no tail.
-__device__ __forceinline__ void hload_batch_s(const char* __restrict__ lane_base, const uint2* __restrict__ qp,
-                                              uint64_t pol, HBatch& b) {
+template <bool kSmem>
+__device__ __forceinline__ void hload_batch_s(const char* __restrict__ lane_base, uint32_t lane_base_s,
+                                              const uint2* __restrict__ qp, uint64_t pol, HBatch& b) {
     uint2 k[kHBQ];
 #pragma unroll
     for (int i = 0; i < kHBQ; ++i) k[i] = qp[2 * i];
 #pragma unroll
     for (int i = 0; i < kHBQ; ++i) {
         b.f[i] = k[i].x;
-        b.v[2 * i + 0] = ld_line(lane_base, k[i].x & kHOffMask, pol);
-        b.v[2 * i + 1] = ld_line(lane_base, k[i].y, pol);
+        if (kSmem) {  // offsets are line * 128 here: the low 7 bits carry the flags
+            b.v[2 * i + 0] = ld_line_smem(lane_base_s, k[i].x & ~127u);
+            b.v[2 * i + 1] = ld_line_smem(lane_base_s, k[i].y);
+        } else {
+            b.v[2 * i + 0] = ld_line(lane_base, k[i].x & kHOffMask, pol);
+            b.v[2 * i + 1] = ld_line(lane_base, k[i].y, pol);
+        }
     }
 }
 
@@ -104,18 +121,20 @@ __device__ __forceinline__ void hconsume_batch(const HBatch& b, uint32_t& r0, ui
     }
 }
 
-__device__ __forceinline__ void hand_phase_staged(const char* __restrict__ lane_base, const uint2* __restrict__ qp,
-                                                  uint32_t n_batches, int half, uint64_t pol, uint2* park) {
+template <bool kSmem>
+__device__ __forceinline__ void hand_phase_staged(const char* __restrict__ lane_base, uint32_t lane_base_s,
+                                                  const uint2* __restrict__ qp, uint32_t n_batches, int half,
+                                                  uint64_t pol, uint2* park) {
     if (n_batches == 0) return;
     uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, emitted = 0;
     HBatch A, B;
-    hload_batch_s(lane_base, qp, pol, A);
+    hload_batch_s<kSmem>(lane_base, lane_base_s, qp, pol, A);
 #pragma unroll 1
     while (true) {
-        if (n_batches > 1) hload_batch_s(lane_base, qp + 2 * kHBQ, pol, B);
+        if (n_batches > 1) hload_batch_s<kSmem>(lane_base, lane_base_s, qp + 2 * kHBQ, pol, B);
         hconsume_batch(A, r0, r1, park, emitted, half);
         if (n_batches <= 1) break;
-        if (n_batches > 2) hload_batch_s(lane_base, qp + 4 * kHBQ, pol, A);
+        if (n_batches > 2) hload_batch_s<kSmem>(lane_base, lane_base_s, qp + 4 * kHBQ, pol, A);
         hconsume_batch(B, r0, r1, park, emitted, half);
         if (n_batches <= 2) break;
         n_batches -= 2;
@@ -184,13 +203,23 @@ __global__ void make_policy_kernel(uint64_t* out) {
     *out = pol;
 }
 
-__global__ void __launch_bounds__(kThreads, HT_HALF_MIN_CTAS)
+// kStage: blocks whose keys fall into a run of at most `stage_lines` consecutive keys (blk_key_lo / blk_key_cnt,
+// planner: TransformPlan.block_spans) copy that run of 128-byte lines into shared memory ONCE with cp.async and
+// AND out of shared memory; what crosses L2 -> SM per block is then the run (219 lines on average for the
+// position-sorted UKB-scale plan) instead of one line per haplotype allele (1,406).  Other blocks of the same
+// launch take the L2 path below.  Position-sorted haplotype sets (what `haptools index` produces,
+// haptools/index.py:31-94) are where blocks are key-local.
+template <bool kStage>
+__global__ void __launch_bounds__(kThreads, kStage ? HT_STAGE_MIN_CTAS : HT_HALF_MIN_CTAS)
 transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                          const uint32_t* __restrict__ quad_off16, const uint4* __restrict__ quads,
-                         int64_t n_haps, uint32_t n_hap_blocks, int64_t half0, uint8_t* __restrict__ out,
-                         int64_t out_s_samp, unsigned long long* __restrict__ counts, uint64_t pol) {
+                         const uint32_t* __restrict__ blk_key_lo, const uint32_t* __restrict__ blk_key_cnt,
+                         uint32_t stage_lines, int64_t n_haps, uint32_t n_hap_blocks, int64_t half0,
+                         uint8_t* __restrict__ out, int64_t out_s_samp, unsigned long long* __restrict__ counts,
+                         uint64_t pol) {
     __shared__ __align__(16) uint32_t s_x[kWarps * kXPitch];  // 16.4 KB: parked results, then the exchange
     __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
+    extern __shared__ __align__(128) uint8_t s_stage[];        // kStage: stage_lines * 128 B
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -215,17 +244,54 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
     }
     const uint32_t n_batches = (q_end - q_begin + kHBQ - 1) / kHBQ;
     uint4* my_quads = reinterpret_cast<uint4*>(s_keys) + q_begin + kHBQ * warp;
+    // ---- the block's run of lines -> shared memory (asynchronously; waited for after the quads are staged) ------
+    uint32_t run_lo = 0, run_cnt = 0;
+    if (kStage && staged) {
+        const uint32_t hb = blockIdx.x % n_hap_blocks;
+        run_cnt = __ldg(blk_key_cnt + hb);
+        if (run_cnt > stage_lines) run_cnt = 0;  // block-uniform: 0 = this block reads its lines from L2
+        if (run_cnt) {
+            run_lo = __ldg(blk_key_lo + hb);
+            const char* src = reinterpret_cast<const char*>(planes) +
+                              ((size_t)(ht >> 1) * (size_t)n_keys + run_lo) * (kRecordWords * 4) + (ht & 1) * 128 + 16 * (tid & 7);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + 16 * (tid & 7);
+            for (uint32_t line = tid >> 3; line < run_cnt; line += kThreads / 8)
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + line * 128),
+                             "l"(src + (size_t)line * (kRecordWords * 4)), "l"(pol)
+                             : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
     if (staged && q_begin < q_end) {
         const uint4* srcq = quads + blk_q0 + q_begin;
         const uint32_t nq = q_end - q_begin;
+        const uint32_t lo256 = run_lo << 8;
         for (uint32_t i = lane; i < n_batches * kHBQ; i += 32) {
             uint4 t = __ldg(srcq + min(i, nq - 1));
             if (i >= nq) t.x &= kHOffMask;  // padding: the last quad again, without flags
+            if (kStage && run_cnt) {
+                // record offsets (key * 256) -> offsets into the staged run (line * 128); the quad of a haplotype
+                // without alleles points at record 0, which may lie outside the run: any staged line will do
+                const uint32_t f = t.x & ~kHOffMask;
+                if (f & kHQuadSkip) {
+                    t = make_uint4(f, 0u, 0u, 0u);
+                } else {
+                    t.x = (((t.x & kHOffMask) - lo256) >> 1) | f;
+                    t.y = (t.y - lo256) >> 1;
+                    t.z = (t.z - lo256) >> 1;
+                    t.w = (t.w - lo256) >> 1;
+                }
+            }
             t.z |= t.x & ~kHOffMask;        // both halves of the warp see the flags in their own pair
             my_quads[i] = t;
         }
     }
-    __syncwarp();
+    if (kStage && run_cnt) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // everybody's pieces of the run have landed
+    } else {
+        __syncwarp();
+    }
 
     // ---- 1. AND ----------------------------------------------------------------------------------
     // results are parked in the warp's own exchange row: lane (w, g) keeps haplotypes 8g..8g+7
@@ -233,8 +299,11 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
     if (q_begin < q_end) {
         const char* lane_base = reinterpret_cast<const char*>(planes) +
                                 ((size_t)(ht >> 1) * (size_t)n_keys) * (kRecordWords * 4) + (ht & 1) * 128 + 8 * w;
-        if (staged)
-            hand_phase_staged(lane_base, reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
+        if (kStage && run_cnt)
+            hand_phase_staged<true>(lane_base, (uint32_t)__cvta_generic_to_shared(s_stage) + 8 * w,
+                                    reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
+        else if (staged)
+            hand_phase_staged<false>(lane_base, 0u, reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
         else
             hand_phase_global(lane_base, quads + blk_q0, q_begin, q_end, half, pol, park);
     }
@@ -363,16 +432,27 @@ bool transform_half_enabled() {
 
 int launch_transform_u8_half(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                              const uint32_t* quad_off16, const uint4* quads, int64_t n_haps, uint8_t* out,
-                             int64_t out_s_samp, unsigned long long* counts, cudaStream_t st) {
+                             int64_t out_s_samp, unsigned long long* counts, cudaStream_t st,
+                             const uint32_t* blk_key_lo, const uint32_t* blk_key_cnt, int64_t stage_lines) {
     uint64_t pol = 0;
     if (int rc = l2_policy(&pol, st)) return rc;
     const int64_t n_half = (n_samples + kHalfSamples - 1) / kHalfSamples;
     const int64_t n_hb = (n_haps + kHapBlock - 1) / kHapBlock;
     const int64_t per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
+    const bool stage = blk_key_lo && blk_key_cnt && stage_lines > 0;
+    const size_t smem = stage ? (size_t)stage_lines * 128 : 0;
+    if (stage)  // per launch: the attribute is per device, and a caller may drive several devices from one thread
+        HT_CUDA_TRY(cudaFuncSetAttribute(transform_u8_half_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t t0 = 0; t0 < n_half; t0 += per_launch) {
         const int64_t nt = min(per_launch, n_half - t0);
-        transform_u8_half_kernel<<<dim3((unsigned)(nt * n_hb)), kThreads, 0, st>>>(
-            planes, n_samples, n_keys, quad_off16, quads, n_haps, (uint32_t)n_hb, t0, out, out_s_samp, counts, pol);
+        if (stage)
+            transform_u8_half_kernel<true><<<dim3((unsigned)(nt * n_hb)), kThreads, smem, st>>>(
+                planes, n_samples, n_keys, quad_off16, quads, blk_key_lo, blk_key_cnt, (uint32_t)stage_lines, n_haps,
+                (uint32_t)n_hb, t0, out, out_s_samp, counts, pol);
+        else
+            transform_u8_half_kernel<false><<<dim3((unsigned)(nt * n_hb)), kThreads, 0, st>>>(
+                planes, n_samples, n_keys, quad_off16, quads, nullptr, nullptr, 0u, n_haps, (uint32_t)n_hb, t0, out,
+                out_s_samp, counts, pol);
         HT_CUDA_TRY(cudaGetLastError());
     }
     return HT_OK;

@@ -85,6 +85,15 @@ class DevicePlan:
             _ptr(self.col_key_range), _ptr(self.var_other) if len(var_other) else None, len(var_other),
         )
 
+        # key runs of the 128-haplotype blocks, for the shared-memory staged transform (0 lines: does not pay)
+        env = os.environ.get("HT_STAGE_LINES", "").strip()
+        self.stage_lines = int(env) if env else plan.stage_lines()
+        self.blk_key_lo = self.blk_key_cnt = None
+        if self.stage_lines > 0 and quads is not None:
+            lo, cnt = plan.block_spans()
+            self.blk_key_lo, self.blk_key_cnt = up(lo, np.int32), up(cnt, np.int32)
+        else:
+            self.stage_lines = 0
         self._local = None  # (LocalTables, device tensors, ctypes struct), built on first use
         self._compact = None  # tables for a genotype buffer that holds only the referenced variants
         self._up = up
@@ -180,14 +189,26 @@ def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_pt
     """K2 on raw device pointers.  `counts` (optional int64[H] tensor) receives the number of
     present copies of every haplotype (the numerator of check_maf).
 
-    method  "direct": one kernel, one L2 record read per haplotype allele (ht_transform_u8);
+    method  "direct": one kernel, one L2 line read per haplotype allele (ht_transform_u8);
+            "staged": the same kernel with the key runs of its haplotype blocks staged in shared memory
+            (ht_transform_u8_staged; pays for position-sorted haplotype sets, DevicePlan.stage_lines);
             "local": two phases through shared memory and a bit-packed intermediate
-            (ht_transform_u8_local); "auto": whichever moves fewer bytes through L2 for this
-            plan (DevicePlan.use_local).  Results are identical.
+            (ht_transform_u8_local); "auto": staged when the plan's blocks are key-local, else direct
+            (or local when LOCAL_AUTO is switched on).  Results are identical.
     use_quads  False: let the kernel build its padded key quads from the CSR itself (the form
             without planner support; kept for callers that only have hap_off / hap_key)."""
-    if method not in ("auto", "direct", "local"):
-        raise ValueError("method must be 'auto', 'direct' or 'local'")
+    if method not in ("auto", "direct", "local", "staged"):
+        raise ValueError("method must be 'auto', 'direct', 'staged' or 'local'")
+    if (method == "staged" or method == "auto") and use_quads and dplan.stage_lines > 0:
+        check(
+            _cuda.lib().ht_transform_u8_staged(
+                _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),
+                _ptr(dplan.quad_off16), _ptr(dplan.quads), _ptr(dplan.blk_key_lo), _ptr(dplan.blk_key_cnt),
+                dplan.stage_lines, dplan.n_haps, out_ptr, pitch, _ptr(counts), _stream_ptr(stream),
+            ),
+            "ht_transform_u8_staged",
+        )
+        return
     if method == "local" or (method == "auto" and dplan.use_local()):
         if dplan.n_haps == 0 or n_samples == 0:
             return
@@ -403,6 +424,35 @@ def _ramped_bounds(n: int, chunk: int, n_devs: int = 1):
         bounds.append((s, min(n, s + chunk)))
         s += chunk
     return bounds
+
+
+# Result arrays of transform_host(out=None): like the reference's np.empty (haplotypes.py:1408), except that the
+# memory of a result the caller has DROPPED is handed out again.  A fresh multi-GB np.empty is first touched
+# page by page while it is filled (the kernel zeroes every page: 30 ms of the 72 ms a 3.3 GB result takes), and
+# glibc gives such blocks back to the kernel on free, so a loop of transforms pays that every time.  An owner
+# array is idle when nothing but this list refers to it (every view holds a reference to its base); at most one
+# idle buffer is kept.  HAPTOOLS_B200_RESULT_POOL=0 switches the recycling off.
+_result_owners: list = []
+
+
+def _result_array(shape) -> np.ndarray:
+    import sys
+
+    nbytes = int(np.prod(shape))
+    if os.environ.get("HAPTOOLS_B200_RESULT_POOL", "1").strip() in ("0", "off", "no") or nbytes < (64 << 20):
+        return np.empty(shape, dtype=np.uint8)
+    pick = None
+    for i in range(len(_result_owners) - 1, -1, -1):
+        if sys.getrefcount(_result_owners[i]) > 2:  # the list + getrefcount's argument: views are alive
+            continue
+        owner = _result_owners.pop(i)
+        if pick is None and nbytes <= owner.nbytes <= 2 * nbytes:
+            pick = owner
+        del owner  # idle buffers that do not fit are released
+    if pick is None:
+        pick = np.empty(nbytes, dtype=np.uint8)
+    _result_owners.append(pick)
+    return pick[:nbytes].reshape(shape)
 
 
 def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
@@ -689,7 +739,7 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
         # more than it saves in ONE call (3.3 GB: 1.66 s to allocate + 63 ms, against 314 ms with the staged
         # download into pageable memory, profiles/exp_first_call.py).  pin_output=True, or a page-locked `out`
         # that is reused (bench.py), gives the full PCIe rate.
-        out = pinned_empty((n, H, 2)) if pin_output else np.empty((n, H, 2), dtype=np.uint8)
+        out = pinned_empty((n, H, 2)) if pin_output else _result_array((n, H, 2))
     elif out.shape != (n, H, 2) or out.dtype.itemsize != 1 or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous 1-byte array of shape (n, H, 2)")
     view = out.view(np.bool_)

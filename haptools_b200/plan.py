@@ -131,6 +131,54 @@ class TransformPlan:
         quad_off16 = (qoff[np.minimum(np.arange(0, H + 16, 16), H)] // 4)[: (H + 15) // 16 + 1]
         return quad_off16.astype(np.uint32), val.astype(np.uint32).reshape(-1, 4)
 
+    def block_spans(self, block: int = 128):
+        """
+        Key run of every block of `block` consecutive haplotypes (caller's order; the unit one CTA of the
+        transform kernel handles): returns (blk_key_lo, blk_key_cnt), uint32 arrays of ceil(H / block) entries
+        with cnt = max key - min key + 1 over the block's lists (0 for a block without keys).  Keys are numbered
+        by variant column, so position-sorted haplotype sets (`haptools index`, haptools/index.py:31-94) have
+        short runs; ht_transform_u8_staged stages them in shared memory.
+        """
+        H = self.n_haps
+        nb = (H + block - 1) // block
+        lo = np.zeros(nb, dtype=np.int64)
+        cnt = np.zeros(nb, dtype=np.int64)
+        if self.n_refs:
+            off = self.hap_off.astype(np.int64)
+            key = self.hap_key.astype(np.int64)
+            first = off[np.minimum(np.arange(nb) * block, H)]
+            last = off[np.minimum((np.arange(nb) + 1) * block, H)]
+            has = last > first
+            starts = first[has]  # consecutive non-empty starts delimit exactly the blocks' reference ranges
+            mn = np.minimum.reduceat(key, starts)
+            mx = np.maximum.reduceat(key, starts)
+            lo[has] = mn
+            cnt[has] = mx - mn + 1
+        return lo.astype(np.uint32), cnt.astype(np.uint32)
+
+    def stage_lines(self, max_lines: int = 608, block: int = 128) -> int:
+        """
+        Shared-memory budget (in 128-byte lines) worth giving ht_transform_u8_staged for this plan, or 0 when
+        staging does not pay: the smallest multiple of 32 that lets the blocks holding >= 95 % of the haplotype
+        alleles stage their runs, provided those runs are at most half as many lines as the L2 reads they replace.
+        """
+        if self.n_refs == 0 or self.n_haps == 0:
+            return 0
+        _, cnt = self.block_spans(block)
+        cnt = cnt.astype(np.int64)
+        off = self.hap_off.astype(np.int64)
+        nb = len(cnt)
+        refs = off[np.minimum((np.arange(nb) + 1) * block, self.n_haps)] - off[np.minimum(np.arange(nb) * block, self.n_haps)]
+        order = np.argsort(cnt, kind="stable")
+        covered = np.cumsum(refs[order])
+        k = int(np.searchsorted(covered, 0.95 * self.n_refs, side="left"))
+        need = int(cnt[order[min(k, nb - 1)]])
+        lines = (need + 31) // 32 * 32
+        if lines == 0 or lines > max_lines:
+            return 0
+        ok = cnt <= lines
+        return lines if 2 * int(cnt[ok].sum()) <= int(refs[ok].sum()) else 0
+
     def key_col(self) -> np.ndarray:
         """Column of each key, (A,) uint32."""
         return np.repeat(self.var_col, np.diff(self.var_key_off.astype(np.int64)))

@@ -201,6 +201,24 @@ int ht_transform_u8(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                     uint64_t* counts, void* stream);
 
 /*
+ * K2 with the key runs of the haplotype blocks: haplotypes that are neighbours in the caller's order usually
+ * refer to neighbouring variants -- a .hap file that went through `haptools index` (haptools/index.py:31-94) is
+ * sorted by position -- so the keys of the 128 haplotypes one CTA handles fall into a short run of consecutive
+ * keys.  blk_key_lo[b] / blk_key_cnt[b] (DEVICE arrays, ceil(H / 128) entries; planner: TransformPlan.block_spans)
+ * give that run for block b (cnt 0: the block has no keys).  A block whose run has at most `stage_lines`
+ * (<= HT_STAGE_LINES_MAX) keys copies the run's 128-byte lines into shared memory once (cp.async) and ANDs out
+ * of shared memory instead of reading one line from L2 per haplotype allele; other blocks of the same launch
+ * take ht_transform_u8's path.  Needs the quads and 16-byte aligned rows (else, and with stage_lines == 0, this
+ * IS ht_transform_u8).  Same result bytes.  Shared memory per CTA: 28.4 KB + stage_lines * 128 B.
+ */
+#define HT_STAGE_LINES_MAX 1536
+int ht_transform_u8_staged(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                           const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* quad_off16,
+                           const uint32_t* quads, const uint32_t* blk_key_lo, const uint32_t* blk_key_cnt,
+                           int64_t stage_lines, int64_t n_haps, uint8_t* out, int64_t out_s_samp,
+                           uint64_t* counts, void* stream);
+
+/*
  * K2, bit-packed result: out_bits has the plane layout with haplotypes in place of keys
  * (out_bits[tile][hap][word][strand]); 1/8 of the bytes of the uint8 form, used for the
  * optional all-gather across sample shards and for device-side consumers.  Feeding it
