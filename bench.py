@@ -525,13 +525,14 @@ def stream_workload(c, args):
         st = {}
         res = stream.transform_pgen_stream(reader, idx, n, plan, chunk_variants=chunk, stats=st, to_host=False)
         torch.cuda.synchronize()
-        if best is None or st["stream_s"] < best["stream_s"]:
+        if best is None or st["packed_s"] < best["packed_s"]:
             best = st
     # parity of a slice: the oracle on the same pattern (variant v = pattern row v % 64, -9 -> 255)
     cols = plan.var_col.astype(np.int64)
     ns = 64
-    sub = base[:ns, cols % rows].copy()
-    sub[pool[cols % rows][:, : 2 * ns].reshape(len(cols), ns, 2).transpose(1, 0, 2) == -9] = 255
+    pat = np.arange(len(cols)) % rows  # only referenced variants are read: the j-th of them receives pattern row j % 64
+    sub = base[:ns, pat].copy()
+    sub[pool[pat][:, : 2 * ns].reshape(len(cols), ns, 2).transpose(1, 0, 2) == -9] = 255
     want = orc.transform_from_csr(sub, np.searchsorted(cols, plan.key_col().astype(np.int64)), plan.key_allele,
                                   plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
     got = res[:ns].cpu().numpy().view(np.bool_)
@@ -546,10 +547,11 @@ def stream_workload(c, args):
         "value": n * Hs * 2 / wall, "unit": UNIT, "ms": wall * 1e3, "samples": n, "variants_in_slice": V, "haplotypes_in_slice": Hs,
         "chunks": best["chunks"], "chunk_variants": chunk, "h2d_bytes": best["h2d_bytes"], "h2d_GBps": h2d_gbs,
         "pack_i32_GBps": pack_gbs, "reader_s": best["read_s"], "h2d_s": best["h2d_s"], "pack_s": best["pack_s"],
-        "stream_wall_s": best["stream_s"],
-        "overlap_efficiency": max(best["read_s"], best["h2d_s"], best["pack_s"]) / best["stream_s"],
+        "stream_wall_s": best["packed_s"],
+        # wall = until the last chunk has been packed (the host loop itself only ENQUEUES: its end is not the end)
+        "overlap_efficiency": max(best["read_s"], best["h2d_s"], best["pack_s"]) / best["packed_s"],
         "bound": "PCIe H2D of int32 alleles (4 bytes per allele call: 16x the bytes of the bit-planes they become)",
-        "full_config_estimate_s": best["stream_s"] / best["chunks"] * full_chunks,
+        "full_config_estimate_s": best["packed_s"] / best["chunks"] * full_chunks,
         "verified_against_oracle": verified,
         "workload": w["name"] + f"; bounded sample: its first {args.stream_chunks} chunks ({V} variants) and the {Hs} haplotypes inside them",
         "launches": best["chunks"] + 1,

@@ -269,10 +269,11 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
         for (uint32_t i = lane; i < n_batches * kHBQ; i += 32) {
             uint4 t = __ldg(srcq + min(i, nq - 1));
             if (i >= nq) t.x &= kHOffMask;  // padding: the last quad again, without flags
+            const uint32_t f = t.x & ~kHOffMask;
             if (kStage && run_cnt) {
-                // record offsets (key * 256) -> offsets into the staged run (line * 128); the quad of a haplotype
-                // without alleles points at record 0, which may lie outside the run: any staged line will do
-                const uint32_t f = t.x & ~kHOffMask;
+                // record offsets (key * 256) -> offsets into the staged run (line * 128: bit 7 now belongs to the
+                // offset, the flags keep bits 0-1); the quad of a haplotype without alleles points at record 0,
+                // which may lie outside the run: any staged line will do
                 if (f & kHQuadSkip) {
                     t = make_uint4(f, 0u, 0u, 0u);
                 } else {
@@ -282,7 +283,7 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
                     t.w = (t.w - lo256) >> 1;
                 }
             }
-            t.z |= t.x & ~kHOffMask;        // both halves of the warp see the flags in their own pair
+            t.z |= f;  // both halves of the warp see the flags in their own pair
             my_quads[i] = t;
         }
     }

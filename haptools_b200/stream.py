@@ -87,6 +87,7 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
         h2d_bytes = 0
         timing = stats is not None
         ev_pairs = []  # (h2d start, h2d end, pack start, pack end) CUDA events per chunk
+        ev_start = s_in.record_event(torch.cuda.Event(enable_timing=True)) if timing else None
         for k, v0 in enumerate(range(0, V, chunk)):
             v1 = min(V, v0 + chunk)
             c = v1 - v0
@@ -115,7 +116,8 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
             ev_pack[db] = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else s_cmp.record_event()
             if timing:
                 ev_pairs.append((e0, ev_h2d[hb], e2, ev_pack[db]))
-        t_packed = time.perf_counter()
+        t_packed = time.perf_counter()  # everything ENQUEUED; the copies and packs may still be running
+        ev_packed = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else None
         with torch.cuda.stream(s_cmp):
             if fmt == "bits":
                 tiles = (n + engine.TILE - 1) // engine.TILE
@@ -144,6 +146,10 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
         if stats is not None:
             stats.update(h2d_s=sum(a.elapsed_time(b) for a, b, _, _ in ev_pairs) * 1e-3,
                          pack_s=sum(c.elapsed_time(d) for _, _, c, d in ev_pairs) * 1e-3)
+            ev_packed.synchronize()
+            # packed_s: device time from the first copy's turn on the copy stream to the last pack -- the loop above
+            # only ENQUEUES, so its own end (stream_s) says nothing when the reader is fast
+            stats.update(packed_s=ev_start.elapsed_time(ev_packed) * 1e-3)
             stats.update(read_s=t_read, stream_s=t_packed - t_start, total_device_s=t_done - t_start,
                          total_s=time.perf_counter() - t_start, h2d_bytes=h2d_bytes, chunks=-(-V // chunk) if V else 0)
     return res
