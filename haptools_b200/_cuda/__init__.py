@@ -54,6 +54,7 @@ SIGNATURES = {
     "ht_plane_bytes": (_sz, [_i64, _i64]),
     "ht_pack_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i32, _p]),
     "ht_pack_i32": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "ht_pack_i32_anc": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "ht_transform_u8_staged": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),

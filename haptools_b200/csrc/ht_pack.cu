@@ -122,7 +122,12 @@ struct LoadI32 {
         const int2 v = __ldg(reinterpret_cast<const int2*>(a.gt + (int64_t)col * a.gv) + s);
         const uint32_t b0 = v.x == -9 ? 255u : ((uint32_t)v.x & 0xffu);
         const uint32_t b1 = v.y == -9 ? 255u : ((uint32_t)v.y & 0xffu);
-        return b0 | (b1 << 8);
+        uint32_t x = b0 | (b1 << 8);
+        if (kAnc) {  // local-ancestry labels of the chunk: plain bytes with their own strides (row = `col`)
+            const uint8_t* l = a.anc + s * a.as + (int64_t)col * a.av;
+            x |= ((uint32_t)l[0] << 16) | ((uint32_t)l[a.ac] << 24);
+        }
+        return x;
     }
 };
 
@@ -1509,14 +1514,23 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
                 const uint32_t* var_col, const uint32_t* var_key_off, const uint8_t* key_allele,
                 int64_t n_vars, int64_t key_base, int64_t n_keys_total, uint32_t* planes,
                 uint32_t* flags, void* stream) {
+    return ht_pack_i32_anc(alleles, row_pitch_elems, n_samples, nullptr, 0, 0, 0, var_col, var_key_off, key_allele,
+                           nullptr, n_vars, key_base, n_keys_total, planes, flags, stream);
+}
+
+int ht_pack_i32_anc(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_samples, const uint8_t* anc,
+                    int64_t anc_s_samp, int64_t anc_s_var, int64_t anc_s_strand, const uint32_t* var_col,
+                    const uint32_t* var_key_off, const uint8_t* key_allele, const uint8_t* key_label,
+                    int64_t n_vars, int64_t key_base, int64_t n_keys_total, uint32_t* planes,
+                    uint32_t* flags, void* stream) {
     using namespace ht;
     PackArgs a;
     a.gt = reinterpret_cast<const uint8_t*>(alleles);
     a.gs = 8; a.gv = row_pitch_elems * 4; a.gc = 4;
-    a.anc = nullptr; a.as = a.av = a.ac = 0;
+    a.anc = anc; a.as = anc_s_samp; a.av = anc_s_var; a.ac = anc_s_strand;
     a.n = n_samples;
     a.var_col = var_col; a.var_key_off = var_key_off;
-    a.key_allele = key_allele; a.key_label = nullptr;
+    a.key_allele = key_allele; a.key_label = key_label;
     a.col_var = nullptr; a.col_key01 = nullptr; a.col_key_range = nullptr; a.var_sel = nullptr; a.n_cols = 0;
     a.n_vars = n_vars; a.n_keys = n_keys_total; a.key_base = key_base;
     a.planes = planes; a.flags = flags;
@@ -1525,8 +1539,8 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
     if (row_pitch_elems < 2 * n_samples) return bad_arg("row_pitch_elems < 2 * n_samples");
     if (!aligned(alleles, a.gv, 8)) return bad_arg("int32 allele rows must be 8-byte aligned");
     const int64_t n_vblocks = (n_vars + kPackWarps - 1) / kPackWarps;
-    return launch_tiled(pack_generic_kernel<LoadI32, false>, a, n_vblocks, 0, false,
-                        (cudaStream_t)stream);
+    return anc ? launch_tiled(pack_generic_kernel<LoadI32, true>, a, n_vblocks, 0, false, (cudaStream_t)stream)
+               : launch_tiled(pack_generic_kernel<LoadI32, false>, a, n_vblocks, 0, false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

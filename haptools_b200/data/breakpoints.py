@@ -73,9 +73,14 @@ class Breakpoints:
         pops = np.concatenate(pops) if pops else np.zeros(0, dtype=np.uint8)
         return names, list(chroms), var_key, keys, pops.astype(np.uint8), np.asarray(seg_off, dtype=np.uint32)
 
-    def population_tensor(self, variants: np.ndarray, samples: tuple = None, device=None):
-        """`population_array` as a CUDA uint8 tensor (n, p, 2) that never visits the host --
-        what the ancestry pack kernel consumes."""
+    def population_provider(self, variants: np.ndarray, samples: tuple = None, device=None):
+        """The device side of `population_array`, column chunk by column chunk: returns an object whose
+        `labels(cols)` launches ht_bp_ancestry for the variants `variants[cols]` and returns their labels as a CUDA
+        uint8 tensor `(n, len(cols), 2)` (asynchronous on the current stream), and whose `check()` raises the
+        reference's ValueError if some (sample, strand, variant) had no block (haptools/data/breakpoints.py:
+        296-323).  The block tables are uploaded once.  This is what the streamed PGEN path asks for chunk by
+        chunk (stream.transform_pgen_stream), so the `(n, p, 2)` ancestry matrix the reference materialises
+        (haptools/transform.py:658) never exists."""
         import torch
 
         from .. import _cuda, engine
@@ -87,33 +92,78 @@ class Breakpoints:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         n, p = len(names), len(variants)
         self.log.info(f"Obtaining ancestry for {n} samples and {p} variants in {len(chroms)} chromosomes")
-        with torch.cuda.device(dev):
-            up = lambda a, t: torch.from_numpy(np.ascontiguousarray(a).view(t)).to(dev)  # noqa: E731
-            d_keys, d_pops = up(keys, np.int64), up(pops, np.uint8)
-            d_seg, d_var = up(seg_off, np.int32), up(var_key, np.int64)
-            anc = torch.empty((n, p, 2), dtype=torch.uint8, device=dev)
-            bad = torch.full((1,), -1, dtype=torch.int64, device=dev)
-            _cuda.check(
-                _cuda.lib().ht_bp_ancestry(
-                    d_keys.data_ptr(), d_pops.data_ptr(), d_seg.data_ptr(), d_var.data_ptr(), anc.data_ptr(),
-                    *anc.stride(), n, p, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                "ht_bp_ancestry",
-            )
-            code = int(bad.item())
-        if code != -1:
-            strand_idx, v = (code >> 32) & 0xFFFFFFFF, code & 0xFFFFFFFF
-            samp, strand = names[strand_idx // 2], strand_idx % 2
-            chrom = str(variants["chrom"][v])
-            blocks = (self.data if samples is None else {s: self.data[s] for s in samples})[samp][strand]
-            if not np.any(blocks["chrom"] == chrom):
+        owner = self
+
+        class Provider:
+            n_samples = n
+
+            def __init__(self):
+                with torch.cuda.device(dev):
+                    up = lambda a, t: torch.from_numpy(np.ascontiguousarray(a).view(t)).to(dev)  # noqa: E731
+                    self.d_keys, self.d_pops = up(keys, np.int64), up(pops, np.uint8)
+                    self.d_seg, self.d_var = up(seg_off, np.int32), up(var_key, np.int64)
+                    self.bad = torch.full((1,), -1, dtype=torch.int64, device=dev)
+                    # chunk-local failure word: (strand index << 32 | chunk column); translated back on the host
+                    self.pending = []
+
+            def labels(self, cols=None, variant_major: bool = False):
+                with torch.cuda.device(dev):
+                    if cols is None:
+                        d_var, c = self.d_var, p
+                    else:
+                        idx = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(dev)
+                        d_var, c = self.d_var[idx], len(cols)
+                    if variant_major:  # (c, n, 2) memory, seen as (n, c, 2): the layout of a pgenlib chunk
+                        anc = torch.empty((c, n, 2), dtype=torch.uint8, device=dev).permute(1, 0, 2)
+                    else:
+                        anc = torch.empty((n, c, 2), dtype=torch.uint8, device=dev)
+                    bad = torch.full((1,), -1, dtype=torch.int64, device=dev)
+                    _cuda.check(
+                        _cuda.lib().ht_bp_ancestry(
+                            self.d_keys.data_ptr(), self.d_pops.data_ptr(), self.d_seg.data_ptr(), d_var.data_ptr(),
+                            anc.data_ptr(), *anc.stride(), n, c, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "ht_bp_ancestry",
+                    )
+                    self.pending.append((bad, None if cols is None else np.asarray(cols, dtype=np.int64), d_var))
+                    return anc
+
+            def check(self):
+                """Raise for the first (strand, variant) without a block, in the reference's order of discovery
+                (sample by sample, strand by strand: the minimum strand index, then the minimum variant)."""
+                worst = None
+                for bad, cols, _ in self.pending:
+                    code = int(bad.item())
+                    if code == -1:
+                        continue
+                    strand_idx, v = (code >> 32) & 0xFFFFFFFF, code & 0xFFFFFFFF
+                    v = int(cols[v]) if cols is not None else v
+                    if worst is None or (strand_idx, v) < worst:
+                        worst = (strand_idx, v)
+                self.pending = []
+                if worst is None:
+                    return
+                strand_idx, v = worst
+                samp, strand = names[strand_idx // 2], strand_idx % 2
+                chrom = str(variants["chrom"][v])
+                blocks = (owner.data if samples is None else {s: owner.data[s] for s in samples})[samp][strand]
+                if not np.any(blocks["chrom"] == chrom):
+                    raise ValueError(
+                        f"Chromosome {chrom} in the genotypes is absent in the breakpoints for sample "
+                        f"{samp}_{strand + 1}. Check that your 'chr' prefixes match!"
+                    )
                 raise ValueError(
-                    f"Chromosome {chrom} in the genotypes is absent in the breakpoints for sample "
-                    f"{samp}_{strand + 1}. Check that your 'chr' prefixes match!"
+                    f"The breakpoints for chromosome {chrom} in sample {samp}_{strand + 1} do not specify an "
+                    "ancestry for one of the requested variants."
                 )
-            raise ValueError(
-                f"The breakpoints for chromosome {chrom} in sample {samp}_{strand + 1} do not specify an "
-                "ancestry for one of the requested variants."
-            )
+
+        return Provider()
+
+    def population_tensor(self, variants: np.ndarray, samples: tuple = None, device=None):
+        """`population_array` as a CUDA uint8 tensor (n, p, 2) that never visits the host --
+        what the ancestry pack kernel consumes."""
+        provider = self.population_provider(variants, samples, device)
+        anc = provider.labels()
+        provider.check()
         return anc
 
     def population_array(self, variants: np.ndarray, samples: tuple = None) -> np.ndarray:

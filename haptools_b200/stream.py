@@ -46,11 +46,37 @@ class ArrayPgenReader:
             np.take(self._alleles, variant_idxs, axis=0, out=allele_int32_out)
 
 
+def _ancestry_chunks(ancestry, n: int, p: int, dev):
+    """Normalise the `ancestry` argument of transform_pgen_stream into `labels(cols) -> CUDA uint8 (n, c, 2)`
+    (launched on the current stream) and `check()`."""
+    if hasattr(ancestry, "labels") and hasattr(ancestry, "check"):  # Breakpoints.population_provider
+        if ancestry.n_samples != n:
+            raise ValueError("the breakpoints and the genotypes differ in their samples")
+        return (lambda cols: ancestry.labels(cols, variant_major=True)), ancestry.check
+    if callable(ancestry):
+        return ancestry, (lambda: None)
+    if isinstance(ancestry, torch.Tensor):
+        if not ancestry.is_cuda or ancestry.dtype != torch.uint8 or tuple(ancestry.shape[:2]) != (n, p) or ancestry.shape[2] < 2:
+            raise ValueError("ancestry must be a CUDA uint8 tensor shaped (samples, variants, 2)")
+        return (lambda cols: ancestry.index_select(1, torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(dev))), (lambda: None)
+    a = np.asarray(ancestry)
+    if a.dtype != np.uint8 or a.shape[:2] != (n, p) or a.shape[2] < 2:
+        raise ValueError("ancestry must be a uint8 array shaped (samples, variants, 2)")
+    # a host matrix (GenotypesAncestry.ancestry): the chunk's columns are gathered on the host and uploaded
+    return (lambda cols: torch.from_numpy(np.ascontiguousarray(a[:, cols, :2])).to(dev, non_blocking=False)), (lambda: None)
+
+
 def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan: TransformPlan,
                           chunk_variants: int = 1024, device=None, n_host_buffers: int = 3,
-                          fmt: str = "u8", to_host: bool = True, stats: dict = None):
+                          fmt: str = "u8", to_host: bool = True, stats: dict = None, ancestry=None):
     """
     reader        object with pgenlib's `read_alleles_list(idx, int32[c, 2n])`
+    ancestry      for ancestry plans (what `transform --ancestry` does on PGEN input, haptools/transform.py:
+                  610-660): where the local-ancestry labels of a chunk's variants come from -- a
+                  `Breakpoints.population_provider(...)` (labels computed on the device from the .bp blocks, chunk
+                  by chunk: neither gts.data nor the (n, p, 2) ancestry matrix is ever built), a `(n, p, 2)` uint8
+                  matrix (CUDA tensor or host array, columns = the plan's), or any callable
+                  `cols -> CUDA uint8 tensor (n, len(cols), 2)`
     variant_idxs  uint32 indices (into the PGEN) of the variants to read; column j of the plan
                   is variant_idxs[j] (so plan.n_cols == len(variant_idxs))
     Returns the `(n, H, 2)` bool result (numpy if `to_host`, else a device uint8 tensor), or the
@@ -61,10 +87,11 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
     p = len(variant_idxs)
     if p != plan.n_cols:
         raise ValueError(f"plan was made for {plan.n_cols} variant columns, {p} variants are to be read")
-    if plan.has_ancestry:
-        raise ValueError("local ancestry is not part of the PGEN stream")
+    if plan.has_ancestry != (ancestry is not None):
+        raise ValueError("ancestry plan and ancestry source must be given together")
     n, H = int(n_samples), plan.n_haps
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    anc_labels, anc_check = _ancestry_chunks(ancestry, n, p, dev) if ancestry is not None else (None, None)
     lib = _cuda.lib()
     t_start = time.perf_counter()
     with torch.cuda.device(dev):
@@ -107,12 +134,26 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
             ev_h2d[hb] = s_in.record_event(torch.cuda.Event(enable_timing=True)) if timing else s_in.record_event()
             s_cmp.wait_event(ev_h2d[hb])
             e2 = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else None
-            check(
-                lib.ht_pack_i32(devbuf[db].data_ptr(), 2 * n, n, row_in_chunk.data_ptr() + 4 * v0,
-                                dplan.var_key_off.data_ptr() + 4 * v0, dplan.key_allele.data_ptr(), c, 0,
-                                plan.n_keys, planes.data_ptr(), 0, s_cmp.cuda_stream),
-                "ht_pack_i32",
-            )
+            if anc_labels is None:
+                check(
+                    lib.ht_pack_i32(devbuf[db].data_ptr(), 2 * n, n, row_in_chunk.data_ptr() + 4 * v0,
+                                    dplan.var_key_off.data_ptr() + 4 * v0, dplan.key_allele.data_ptr(), c, 0,
+                                    plan.n_keys, planes.data_ptr(), 0, s_cmp.cuda_stream),
+                    "ht_pack_i32",
+                )
+            else:
+                with torch.cuda.stream(s_cmp):  # allocated and filled in the compute stream's order
+                    anc_t = anc_labels(cols[v0:v1])
+                if anc_t.dtype != torch.uint8 or tuple(anc_t.shape[:2]) != (n, c):
+                    raise ValueError("the ancestry source must return a CUDA uint8 tensor (samples, chunk variants, 2)")
+                check(
+                    lib.ht_pack_i32_anc(devbuf[db].data_ptr(), 2 * n, n, anc_t.data_ptr(), *map(int, anc_t.stride()),
+                                        row_in_chunk.data_ptr() + 4 * v0, dplan.var_key_off.data_ptr() + 4 * v0,
+                                        dplan.key_allele.data_ptr(), dplan.key_label.data_ptr(), c, 0, plan.n_keys,
+                                        planes.data_ptr(), 0, s_cmp.cuda_stream),
+                    "ht_pack_i32_anc",
+                )
+                anc_t.record_stream(s_cmp)
             ev_pack[db] = s_cmp.record_event(torch.cuda.Event(enable_timing=True)) if timing else s_cmp.record_event()
             if timing:
                 ev_pairs.append((e0, ev_h2d[hb], e2, ev_pack[db]))
@@ -130,6 +171,8 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
                 res = buf[:, : 2 * H].unflatten(1, (H, 2))
         s_cmp.synchronize()
         cur.wait_stream(s_cmp)
+        if anc_check is not None:
+            anc_check()  # e.g. a variant that no breakpoint block covers: the reference's ValueError
         t_done = time.perf_counter()
         if to_host:
             if fmt == "bits":

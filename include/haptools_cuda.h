@@ -168,6 +168,19 @@ int ht_pack_i32(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_sampl
                 int64_t n_keys_total, uint32_t* planes, uint32_t* flags, void* stream);
 
 /*
+ * The same with local ancestry (what `transform --ancestry` does on PGEN input, haptools/transform.py:610-660,
+ * without ever building gts.data or the (n, p, 2) ancestry matrix): `anc` holds the labels of THIS chunk's
+ * variants, element (s, r, c) at anc + s*anc_s_samp + r*anc_s_var + c*anc_s_strand with r the chunk row
+ * (var_col[]), e.g. written by ht_bp_ancestry for the chunk's positions; key_label[] as in ht_pack_tables.
+ * anc == NULL (then key_label must be NULL): ht_pack_i32.
+ */
+int ht_pack_i32_anc(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_samples, const uint8_t* anc,
+                    int64_t anc_s_samp, int64_t anc_s_var, int64_t anc_s_strand, const uint32_t* var_col,
+                    const uint32_t* var_key_off, const uint8_t* key_allele, const uint8_t* key_label,
+                    int64_t n_vars, int64_t key_base, int64_t n_keys_total, uint32_t* planes,
+                    uint32_t* flags, void* stream);
+
+/*
  * K2 -- transform.  Replaces the per-haplotype loop
  * `hap_gts.data[:, i] = np.all(equality_arr[:, idxs[i]], axis=1)` (haplotypes.py:1411-1412;
  * with ancestry folded into the keys also transform.py:144-148).

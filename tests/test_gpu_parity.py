@@ -441,6 +441,75 @@ def test_pgen_stream_many_chunks_ring():
     assert stats["chunks"] == len(calls) == -(-plan.n_vars // 64) and sum(calls) == plan.n_vars
 
 
+@pytest.mark.parametrize("source", ["host_matrix", "device_matrix", "callable"])
+@pytest.mark.parametrize("chunk", [9, 64, 1000])
+def test_pgen_stream_with_ancestry(chunk, source):
+    """`transform --ancestry` on PGEN input (haptools/transform.py:610-660): int32 chunks + the local-ancestry
+    labels of each chunk's variants -> ancestry planes (ht_pack_i32_anc), against the oracle."""
+    rng = np.random.default_rng(23)
+    n, H = 1300, 90
+    gt, anc, plan, want = _random_arrays(rng, n, 150, H, missing=0.03, n_pops=5)
+    rows = gt.transpose(1, 0, 2).reshape(150, 2 * n).astype(np.int32)
+    rows[rows == 255] = -9
+    reader = stream.ArrayPgenReader(rows)
+    src = {"host_matrix": anc, "device_matrix": torch.from_numpy(anc).cuda(),
+           "callable": lambda cols: torch.from_numpy(np.ascontiguousarray(anc[:, cols])).cuda()}[source]
+    got = stream.transform_pgen_stream(reader, np.arange(150, dtype=np.uint32), n, plan, chunk_variants=chunk, ancestry=src)
+    np.testing.assert_array_equal(got, want)
+    with pytest.raises(ValueError, match="given together"):
+        stream.transform_pgen_stream(reader, np.arange(150, dtype=np.uint32), n, plan, chunk_variants=chunk)
+
+
+def test_pgen_stream_with_breakpoints_on_the_device():
+    """The whole of transform_haps' ancestry branch without its two big host arrays: labels come from the .bp blocks
+    on the device, chunk by chunk (Breakpoints.population_provider -> ht_bp_ancestry), genotypes from int32 chunks.
+    Expected: the oracle on the (n, p, 2) matrices the reference would have built (breakpoints oracle + transform
+    oracle)."""
+    from haptools_b200.data.breakpoints import HapBlock
+    from oracle import breakpoints_oracle as borc
+
+    rng = np.random.default_rng(29)
+    n, p, H, pops = 700, 260, 120, ("YRI", "CEU", "PEL")
+    bps = data.Breakpoints(fname=None)
+    bps.data = {}
+    for s in range(n):
+        strands = []
+        for c in range(2):
+            k = int(rng.integers(1, 6))
+            ends = np.sort(rng.choice(np.arange(10, 5000), size=k, replace=False))
+            ends[-1] = 5000
+            strands.append(np.array([(str(rng.choice(pops)), "1", int(e), e / 1e4) for e in ends], dtype=HapBlock))
+        bps.data[f"S{s}"] = strands
+    bps.encode(labels=pops)
+    variants = np.zeros(p, dtype=[("chrom", "U10"), ("pos", np.uint32)])
+    variants["chrom"], variants["pos"] = "1", np.sort(rng.choice(np.arange(1, 5001), size=p, replace=False))
+    anc = borc.population_array(bps.data, variants)
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.02] = 255
+    k = rng.integers(1, 5, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    hap_label = rng.integers(0, len(pops), size=H)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, np.repeat(hap_label, k))
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    want = orc.transform_core(gt[:, ref_col], ref_allele.astype(np.uint8), idxs, anc[:, ref_col], hap_label.astype(np.uint8))
+    rows = gt.transpose(1, 0, 2).reshape(p, 2 * n).astype(np.int32)
+    rows[rows == 255] = -9
+    reader = stream.ArrayPgenReader(rows)
+    for chunk in (17, 4096):
+        provider = bps.population_provider(variants)
+        got = stream.transform_pgen_stream(reader, np.arange(p, dtype=np.uint32), n, plan, chunk_variants=chunk, ancestry=provider)
+        np.testing.assert_array_equal(got, want)
+    assert want.any()
+    # a variant beyond every block: the reference's error, raised after the stream
+    far = variants.copy()
+    far["pos"][int(plan.var_col[3])] = 6000
+    with pytest.raises(ValueError, match="do not specify an ancestry"):
+        stream.transform_pgen_stream(reader, np.arange(p, dtype=np.uint32), n, plan, chunk_variants=64,
+                                     ancestry=bps.population_provider(far))
+
+
 # ------------------------------------------------------------------ host pipeline
 @pytest.mark.parametrize("lay", ["C", "F", "C3", "F3"])
 def test_host_pipeline_chunked(lay):
@@ -560,6 +629,52 @@ def test_config_ukb_scale_shard_slice_and_checksums():
         want = orc.transform_from_csr(sub, plan.key_col().astype(np.int64), plan.key_allele,
                                       plan.hap_off.astype(np.int64), plan.hap_key.astype(np.int64))
         np.testing.assert_array_equal(out[s0 : s0 + 64].cpu().numpy().view(np.bool_), want)
+
+
+def test_config_ancestry_scale_slices_and_checksums():
+    """BASELINE configs[3] at its stated shape: 100k samples x 200k variants x 50k haplotypes,
+    5 populations -- GT 40 GB + ANC 40 GB resident in HBM, generated on the device; the oracle (haptools/
+    transform.py:137-148 restated) on three 64-sample slices regenerated on the host from the same hash, and the
+    size-independent checks on everything: bytes are 0/1, fused counts == column sums == popcount of the packed
+    result, and dropping the ancestry condition can only add presence."""
+    n, p, H, n_pops = 100_000, 200_000, 50_000, 5
+    free = torch.cuda.mem_get_info()[0]
+    if free < 115 << 30:
+        n = 25_000  # a quarter of the cohort on a smaller / busier device; same plan, same checks
+    plan = synth.synth_plan(p, H, seed=4, n_pops=n_pops)
+    dplan = engine.DevicePlan(plan)
+    lib = _cuda.lib()
+    gt = torch.empty((n, p, 2), dtype=torch.uint8, device="cuda")
+    anc = torch.empty((n, p, 2), dtype=torch.uint8, device="cuda")
+    _cuda.check(lib.ht_synth_gt(gt.data_ptr(), *gt.stride(), n, p, 0, 5, 1, 0, 0), "synth")
+    _cuda.check(lib.ht_synth_ancestry(anc.data_ptr(), *anc.stride(), n, p, 0, 6, n_pops, 2000, 0), "synth_anc")
+    counts = torch.empty(H, dtype=torch.int64, device="cuda")
+    out = engine.transform_device(gt, dplan, ancestry=anc, counts=counts)
+    torch.cuda.synchronize()
+    assert out.max().item() <= 1
+    sums = torch.zeros(H, dtype=torch.int64, device="cuda")
+    for lo in range(0, n, 20_000):
+        sums += out[lo: lo + 20_000].sum(dim=(0, 2), dtype=torch.int64)
+    assert torch.equal(counts, sums) and int(sums.sum()) > 0
+    bits = engine.transform_device(gt, dplan, ancestry=anc, fmt="bits")
+    assert torch.equal(engine.count_bits(bits, n, H), sums)
+    del bits
+    # the oracle on slices: first, middle, last samples
+    ref_col, ref_allele, hap_off, hap_label = synth.synth_haplotype_refs(p, H, 4, n_pops=n_pops)
+    plain = plan_from_refs(ref_col, ref_allele, hap_off, p)
+    cols = plain.var_col.astype(np.int64)
+    key_in_sub = np.searchsorted(cols, plain.key_col().astype(np.int64))
+    for s0 in (0, n // 2 + 37, n - 64):
+        sub = synth.synth_gt(64, p, 5, mode=1, sample_offset=s0, variants=cols)
+        sub_anc = synth.synth_ancestry(64, p, 6, n_pops, 2000, sample_offset=s0, variants=cols)
+        want = orc.transform_from_csr(sub, key_in_sub, plain.key_allele, plain.hap_off.astype(np.int64),
+                                      plain.hap_key.astype(np.int64), sub_anc, hap_label.astype(np.uint8))
+        np.testing.assert_array_equal(out[s0: s0 + 64].cpu().numpy().view(np.bool_), want)
+        assert want.any()
+    # monotonicity: the plain transform of the same genotypes is present wherever the ancestry-aware one is
+    m = min(n, 8192)
+    plain_out = engine.transform_device(gt[:m], engine.DevicePlan(plain))
+    assert bool(((out[:m] & ~plain_out) == 0).all()) and int(plain_out.sum()) >= int(out[:m].sum())
 
 
 def test_host_pipeline_round_robin_over_devices():
