@@ -268,21 +268,24 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
         const uint32_t lo256 = run_lo << 8;
         for (uint32_t i = lane; i < n_batches * kHBQ; i += 32) {
             uint4 t = __ldg(srcq + min(i, nq - 1));
-            if (i >= nq) t.x &= kHOffMask;  // padding: the last quad again, without flags
-            const uint32_t f = t.x & ~kHOffMask;
+            uint32_t f = t.x & ~kHOffMask;
+            const bool skip = (f & kHQuadSkip) != 0u;  // the one quad of a haplotype without alleles
+            if (i >= nq) f = 0u;                       // padding: the warp's last quad again, without flags
+            t.x &= kHOffMask;
             if (kStage && run_cnt) {
                 // record offsets (key * 256) -> offsets into the staged run (line * 128: bit 7 now belongs to the
-                // offset, the flags keep bits 0-1); the quad of a haplotype without alleles points at record 0,
-                // which may lie outside the run: any staged line will do
-                if (f & kHQuadSkip) {
-                    t = make_uint4(f, 0u, 0u, 0u);
+                // offset, the flags keep bits 0-1).  The quad of a haplotype without alleles points at record 0,
+                // which may lie outside the run (and so does a padding copy of it): any staged line will do
+                if (skip) {
+                    t = make_uint4(0u, 0u, 0u, 0u);
                 } else {
-                    t.x = (((t.x & kHOffMask) - lo256) >> 1) | f;
+                    t.x = (t.x - lo256) >> 1;
                     t.y = (t.y - lo256) >> 1;
                     t.z = (t.z - lo256) >> 1;
                     t.w = (t.w - lo256) >> 1;
                 }
             }
+            t.x |= f;
             t.z |= f;  // both halves of the warp see the flags in their own pair
             my_quads[i] = t;
         }

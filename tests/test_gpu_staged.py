@@ -69,8 +69,8 @@ def _run(gt, plan, stage_lines, method="staged", counts=False, extra_pitch=0):
 SHAPES = [
     # n, p, H, max_k, window, empty_every, wild_every
     (1, 40, 1, 3, 16, 0, 0), (511, 300, 127, 6, 40, 0, 0), (512, 300, 128, 6, 40, 5, 0), (513, 600, 129, 8, 60, 0, 0),
-    (1537, 2000, 700, 20, 80, 7, 0), (2504, 5000, 1000, 20, 80, 0, 97), (3000, 900, 260, 12, 900, 0, 0),
-    (700, 4000, 515, 20, 100, 3, 130),
+    (1537, 2000, 700, 20, 80, 7, 0), (2504, 400, 1000, 20, 80, 0, 300), (3000, 900, 260, 12, 900, 0, 0),
+    (700, 4000, 515, 20, 100, 3, 130), (1100, 300, 640, 9, 30, 16, 0), (600, 200, 384, 3, 20, 2, 0),
 ]
 
 
