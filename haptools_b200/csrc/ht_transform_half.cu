@@ -47,6 +47,10 @@ constexpr uint32_t kHQuadLast = 1u, kHQuadSkip = 2u, kHOffMask = 0xffffff00u;
 #ifndef HT_STAGE_MIN_CTAS
 #define HT_STAGE_MIN_CTAS 3
 #endif
+#ifndef HT_HALF_PER_CTA
+#define HT_HALF_PER_CTA 1
+#endif
+constexpr int kHalfPerCta = HT_HALF_PER_CTA;  // consecutive half tiles one CTA handles
 constexpr int kHBQ = HT_HALF_BQ;  // quads per batch: 2 * kHBQ loads (of 2 x 128 B) in flight per batch
 
 __device__ __forceinline__ uint2 ld_line(const char* lane_base, uint32_t off, uint64_t pol) {
@@ -203,153 +207,15 @@ __global__ void make_policy_kernel(uint64_t* out) {
     *out = pol;
 }
 
-// kStage: blocks whose keys fall into a run of at most `stage_lines` consecutive keys (blk_key_lo / blk_key_cnt,
-// planner: TransformPlan.block_spans) copy that run of 128-byte lines into shared memory ONCE with cp.async and
-// AND out of shared memory; what crosses L2 -> SM per block is then the run (219 lines on average for the
-// position-sorted UKB-scale plan) instead of one line per haplotype allele (1,406).  Other blocks of the same
-// launch take the L2 path below.  Position-sorted haplotype sets (what `haptools index` produces,
-// haptools/index.py:31-94) are where blocks are key-local.
-template <bool kStage>
-__global__ void __launch_bounds__(kThreads, kStage ? HT_STAGE_MIN_CTAS : HT_HALF_MIN_CTAS)
-transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
-                         const uint32_t* __restrict__ quad_off16, const uint4* __restrict__ quads,
-                         const uint32_t* __restrict__ blk_key_lo, const uint32_t* __restrict__ blk_key_cnt,
-                         uint32_t stage_lines, int64_t n_haps, uint32_t n_hap_blocks, int64_t half0,
-                         uint8_t* __restrict__ out, int64_t out_s_samp, unsigned long long* __restrict__ counts,
-                         uint64_t pol) {
-    __shared__ __align__(16) uint32_t s_x[kWarps * kXPitch];  // 16.4 KB: parked results, then the exchange
-    __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
-    extern __shared__ __align__(128) uint8_t s_stage[];        // kStage: stage_lines * 128 B
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int w = lane & 15, half = lane >> 4;
-    const int64_t ht = half0 + (int64_t)(blockIdx.x / n_hap_blocks);  // half tile: samples [512 ht, 512 ht + 512)
-    const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
-    const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
-    const int hl_begin = warp * kHapsPerWarp;
-    const int hl_end = min(hl_begin + kHapsPerWarp, n_blk_haps);
-    uint32_t* my_row = s_x + warp * kXPitch;
-
-    // ---- the quads of my 16 haplotypes ---------------------------------------------------------
-    // staged at quad index q_begin + kHBQ * warp of s_keys, padded to a multiple of kHBQ quads
-    const int64_t g0 = (h0 >> 4), n16 = (n_haps + kHapsPerWarp - 1) >> 4;
-    const uint32_t blk_q0 = __ldg(quad_off16 + g0);
-    const uint32_t blk_q1 = __ldg(quad_off16 + min(g0 + kWarps, n16));
-    const bool staged = (blk_q1 - blk_q0 + kHBQ * kWarps) * 4u <= (uint32_t)kStageKeys;  // block-uniform
-    uint32_t q_begin = 0, q_end = 0;
-    if (hl_begin < hl_end) {
-        q_begin = __ldg(quad_off16 + g0 + warp) - blk_q0;
-        q_end = __ldg(quad_off16 + g0 + warp + 1) - blk_q0;
-    }
-    const uint32_t n_batches = (q_end - q_begin + kHBQ - 1) / kHBQ;
-    uint4* my_quads = reinterpret_cast<uint4*>(s_keys) + q_begin + kHBQ * warp;
-    // ---- the block's run of lines -> shared memory (asynchronously; waited for after the quads are staged) ------
-    uint32_t run_lo = 0, run_cnt = 0;
-    if (kStage && staged) {
-        const uint32_t hb = blockIdx.x % n_hap_blocks;
-        run_cnt = __ldg(blk_key_cnt + hb);
-        if (run_cnt > stage_lines) run_cnt = 0;  // block-uniform: 0 = this block reads its lines from L2
-        if (run_cnt) {
-            run_lo = __ldg(blk_key_lo + hb);
-            const char* src = reinterpret_cast<const char*>(planes) +
-                              ((size_t)(ht >> 1) * (size_t)n_keys + run_lo) * (kRecordWords * 4) + (ht & 1) * 128 + 16 * (tid & 7);
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + 16 * (tid & 7);
-            for (uint32_t line = tid >> 3; line < run_cnt; line += kThreads / 8)
-                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + line * 128),
-                             "l"(src + (size_t)line * (kRecordWords * 4)), "l"(pol)
-                             : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-    }
-    if (staged && q_begin < q_end) {
-        const uint4* srcq = quads + blk_q0 + q_begin;
-        const uint32_t nq = q_end - q_begin;
-        const uint32_t lo256 = run_lo << 8;
-        for (uint32_t i = lane; i < n_batches * kHBQ; i += 32) {
-            uint4 t = __ldg(srcq + min(i, nq - 1));
-            uint32_t f = t.x & ~kHOffMask;
-            const bool skip = (f & kHQuadSkip) != 0u;  // the one quad of a haplotype without alleles
-            if (i >= nq) f = 0u;                       // padding: the warp's last quad again, without flags
-            t.x &= kHOffMask;
-            if (kStage && run_cnt) {
-                // record offsets (key * 256) -> offsets into the staged run (line * 128: bit 7 now belongs to the
-                // offset, the flags keep bits 0-1).  The quad of a haplotype without alleles points at record 0,
-                // which may lie outside the run (and so does a padding copy of it): any staged line will do
-                if (skip) {
-                    t = make_uint4(0u, 0u, 0u, 0u);
-                } else {
-                    t.x = (t.x - lo256) >> 1;
-                    t.y = (t.y - lo256) >> 1;
-                    t.z = (t.z - lo256) >> 1;
-                    t.w = (t.w - lo256) >> 1;
-                }
-            }
-            t.x |= f;
-            t.z |= f;  // both halves of the warp see the flags in their own pair
-            my_quads[i] = t;
-        }
-    }
-    if (kStage && run_cnt) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // everybody's pieces of the run have landed
-    } else {
-        __syncwarp();
-    }
-
-    // ---- 1. AND ----------------------------------------------------------------------------------
-    // results are parked in the warp's own exchange row: lane (w, g) keeps haplotypes 8g..8g+7
-    uint2* park = reinterpret_cast<uint2*>(my_row) + lane;
-    if (q_begin < q_end) {
-        const char* lane_base = reinterpret_cast<const char*>(planes) +
-                                ((size_t)(ht >> 1) * (size_t)n_keys) * (kRecordWords * 4) + (ht & 1) * 128 + 8 * w;
-        if (kStage && run_cnt)
-            hand_phase_staged<true>(lane_base, (uint32_t)__cvta_generic_to_shared(s_stage) + 8 * w,
-                                    reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
-        else if (staged)
-            hand_phase_staged<false>(lane_base, 0u, reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
-        else
-            hand_phase_global(lane_base, quads + blk_q0, q_begin, q_end, half, pol, park);
-    }
-    __syncwarp();
-    uint32_t a[16];  // a[2*j + c] = haplotype 8*half + j of this warp, strand c; bits over my 32 samples
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint2 r = park[j * 32];
-        a[2 * j] = r.x;
-        a[2 * j + 1] = r.y;
-    }
-    if (counts) {
-        // allele counts for check_maf (haptools/data/genotypes.py:559-625), fused: popcount of my word
-        // of every result, one reduction per half warp and one atomic per haplotype and half tile
-        const int64_t rem = n_samples - ht * kHalfSamples - 32 * (int64_t)w;
-        const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
-        const uint32_t members = half ? 0xffff0000u : 0x0000ffffu;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t c = __reduce_add_sync(members, __popc(a[2 * j] & vm) + __popc(a[2 * j + 1] & vm));
-            const int hl = hl_begin + 8 * half + j;
-            if (w == 0 && hl < hl_end && c) atomicAdd(counts + h0 + hl, (unsigned long long)c);
-        }
-    }
-    __syncwarp();  // everybody has read its parked results: the row is free for the exchange
-
-    // ---- 2. bits over samples -> interleaved bits over (haplotype, strand) ------------------------
-    transpose16x32_dev(a);
-
-    // ---- 3. exchange + expand + store ----------------------------------------------------------------
-    {
-        uint32_t* dst = my_row + half * 16 + w;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) dst[m * 32] = a[m];
-    }
-    __syncthreads();
-
+// Step 3b of the kernel: every thread expands words of the exchange buffer to bytes and stores its 16-byte pieces
+// of the (half tile x 128 haplotypes) result band.
+__device__ __forceinline__ void hstore_phase(const uint32_t* __restrict__ s_x, int tid, int n_blk_haps, int ht,
+                                             int64_t h0, int64_t n_samples, uint8_t* __restrict__ out, int64_t out_s_samp) {
     const int cb = tid & 15;  // 16-byte piece of the 256-byte row band: haplotypes h0 + 8 cb .. + 7
     const int g = tid >> 4;   // word of the half tile: samples 32 g .. 32 g + 31
     const int n_my_haps = min(8, n_blk_haps - 8 * cb);
     if (n_my_haps <= 0) return;
-    const int64_t s_base = ht * kHalfSamples;
+    const int64_t s_base = (int64_t)ht * kHalfSamples;
     const int rows = (int)min((int64_t)kHalfSamples, n_samples - s_base);
     const uint32_t* src = s_x + (cb >> 1) * kXPitch + (cb & 1) * 16 + g;
     uint8_t* p0 = out + 2 * (h0 + 8 * cb) + (s_base + 32 * g) * out_s_samp;
@@ -399,6 +265,163 @@ transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples,
     }
 }
 
+// kStage: blocks whose keys fall into a run of at most `stage_lines` consecutive keys (blk_key_lo / blk_key_cnt,
+// planner: TransformPlan.block_spans) copy that run of 128-byte lines into shared memory ONCE with cp.async and
+// AND out of shared memory; what crosses L2 -> SM per block is then the run (219 lines on average for the
+// position-sorted UKB-scale plan) instead of one line per haplotype allele (1,406).  Other blocks of the same
+// launch take the L2 path below.  Position-sorted haplotype sets (what `haptools index` produces,
+// haptools/index.py:31-94) are where blocks are key-local.
+template <bool kStage, int kHpc>
+__global__ void __launch_bounds__(kThreads, kStage ? HT_STAGE_MIN_CTAS : HT_HALF_MIN_CTAS)
+transform_u8_half_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
+                         const uint32_t* __restrict__ quad_off16, const uint4* __restrict__ quads,
+                         const uint32_t* __restrict__ blk_key_lo, const uint32_t* __restrict__ blk_key_cnt,
+                         uint32_t stage_lines, int64_t n_haps, uint32_t n_hap_blocks, int64_t group0,
+                         uint8_t* __restrict__ out, int64_t out_s_samp, unsigned long long* __restrict__ counts,
+                         uint64_t pol) {
+    __shared__ __align__(16) uint32_t s_x[kWarps * kXPitch];  // 16.4 KB: parked results, then the exchange
+    __shared__ __align__(16) uint32_t s_keys[kStageKeys];      // 12 KB, as uint4 quads
+    extern __shared__ __align__(128) uint8_t s_stage[];        // kStage: stage_lines * 128 B
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int w = lane & 15, half = lane >> 4;
+    // the CTA's `hpc` consecutive half tiles (samples [512 ht, 512 ht + 512)): the key lists are staged once for
+    // all of them, and the stores of one half drain while the next one's records are being ANDed
+    // (32-bit: 2^31 half tiles are 10^12 samples; n_haps < 2^31 * 128 is checked by the launcher's grid limit)
+    const int ht_first = (int)((group0 + (int64_t)(blockIdx.x / n_hap_blocks)) * kHpc);
+    const int n_half = (int)((n_samples + kHalfSamples - 1) / kHalfSamples);
+    const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kHapBlock;
+    const int n_blk_haps = (int)min((int64_t)kHapBlock, n_haps - h0);
+    const int hl_begin = warp * kHapsPerWarp;
+    const int hl_end = min(hl_begin + kHapsPerWarp, n_blk_haps);
+    uint32_t* my_row = s_x + warp * kXPitch;
+
+    // ---- the quads of my 16 haplotypes ---------------------------------------------------------
+    // staged at quad index q_begin + kHBQ * warp of s_keys, padded to a multiple of kHBQ quads
+    const int64_t g0 = (h0 >> 4), n16 = (n_haps + kHapsPerWarp - 1) >> 4;
+    const uint32_t blk_q0 = __ldg(quad_off16 + g0);
+    const uint32_t blk_q1 = __ldg(quad_off16 + min(g0 + kWarps, n16));
+    const bool staged = (blk_q1 - blk_q0 + kHBQ * kWarps) * 4u <= (uint32_t)kStageKeys;  // block-uniform
+    uint32_t q_begin = 0, q_end = 0;
+    if (hl_begin < hl_end) {
+        q_begin = __ldg(quad_off16 + g0 + warp) - blk_q0;
+        q_end = __ldg(quad_off16 + g0 + warp + 1) - blk_q0;
+    }
+    const uint32_t n_batches = (q_end - q_begin + kHBQ - 1) / kHBQ;
+    uint4* my_quads = reinterpret_cast<uint4*>(s_keys) + q_begin + kHBQ * warp;
+    // ---- the block's run of lines -> shared memory (asynchronously; waited for after the quads are staged) ------
+    uint32_t run_lo = 0, run_cnt = 0;
+    if (kStage && staged) {
+        const uint32_t hb = blockIdx.x % n_hap_blocks;
+        run_cnt = __ldg(blk_key_cnt + hb);
+        if (run_cnt > stage_lines) run_cnt = 0;  // block-uniform: 0 = this block reads its lines from L2
+        if (run_cnt) run_lo = __ldg(blk_key_lo + hb);
+    }
+    auto stage_run = [&](int ht) {  // the run's line of half tile `ht` -> shared memory, asynchronously
+        const char* src = reinterpret_cast<const char*>(planes) +
+                          ((size_t)(ht >> 1) * (size_t)n_keys + run_lo) * (kRecordWords * 4) + (ht & 1) * 128 + 16 * (tid & 7);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_stage) + 16 * (tid & 7);
+        for (uint32_t line = tid >> 3; line < run_cnt; line += kThreads / 8)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + line * 128),
+                         "l"(src + (size_t)line * (kRecordWords * 4)), "l"(pol)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (kStage && run_cnt) stage_run(ht_first);
+    if (staged && q_begin < q_end) {
+        const uint4* srcq = quads + blk_q0 + q_begin;
+        const uint32_t nq = q_end - q_begin;
+        const uint32_t lo256 = run_lo << 8;
+        for (uint32_t i = lane; i < n_batches * kHBQ; i += 32) {
+            uint4 t = __ldg(srcq + min(i, nq - 1));
+            uint32_t f = t.x & ~kHOffMask;
+            const bool skip = (f & kHQuadSkip) != 0u;  // the one quad of a haplotype without alleles
+            if (i >= nq) f = 0u;                       // padding: the warp's last quad again, without flags
+            t.x &= kHOffMask;
+            if (kStage && run_cnt) {
+                // record offsets (key * 256) -> offsets into the staged run (line * 128: bit 7 now belongs to the
+                // offset, the flags keep bits 0-1).  The quad of a haplotype without alleles points at record 0,
+                // which may lie outside the run (and so does a padding copy of it): any staged line will do
+                if (skip) {
+                    t = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    t.x = (t.x - lo256) >> 1;
+                    t.y = (t.y - lo256) >> 1;
+                    t.z = (t.z - lo256) >> 1;
+                    t.w = (t.w - lo256) >> 1;
+                }
+            }
+            t.x |= f;
+            t.z |= f;  // both halves of the warp see the flags in their own pair
+            my_quads[i] = t;
+        }
+    }
+    __syncwarp();
+
+#pragma unroll 1
+    for (int it = 0; it < kHpc; ++it) {
+        const int ht = ht_first + it;
+        if (ht >= n_half) break;  // CTA-uniform
+        if (kStage && run_cnt) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // everybody's pieces of this half tile's run have landed
+        }
+
+        // ---- 1. AND ------------------------------------------------------------------------------
+        // results are parked in the warp's own exchange row: lane (w, g) keeps haplotypes 8g..8g+7
+        uint2* park = reinterpret_cast<uint2*>(my_row) + lane;
+        if (q_begin < q_end) {
+            const char* lane_base = reinterpret_cast<const char*>(planes) +
+                                    ((size_t)(ht >> 1) * (size_t)n_keys) * (kRecordWords * 4) + (ht & 1) * 128 + 8 * w;
+            if (kStage && run_cnt)
+                hand_phase_staged<true>(lane_base, (uint32_t)__cvta_generic_to_shared(s_stage) + 8 * w,
+                                        reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
+            else if (staged)
+                hand_phase_staged<false>(lane_base, 0u, reinterpret_cast<const uint2*>(my_quads) + half, n_batches, half, pol, park);
+            else
+                hand_phase_global(lane_base, quads + blk_q0, q_begin, q_end, half, pol, park);
+        }
+        __syncwarp();
+        uint32_t a[16];  // a[2*j + c] = haplotype 8*half + j of this warp, strand c; bits over my 32 samples
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint2 r = park[j * 32];
+            a[2 * j] = r.x;
+            a[2 * j + 1] = r.y;
+        }
+        if (counts) {
+            // allele counts for check_maf (haptools/data/genotypes.py:559-625), fused: popcount of my word
+            // of every result, one reduction per half warp and one atomic per haplotype and half tile
+            const int64_t rem = n_samples - (int64_t)ht * kHalfSamples - 32 * (int64_t)w;
+            const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << (int)rem) - 1u));
+            const uint32_t members = half ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t c = __reduce_add_sync(members, __popc(a[2 * j] & vm) + __popc(a[2 * j + 1] & vm));
+                const int hl = hl_begin + 8 * half + j;
+                if (w == 0 && hl < hl_end && c) atomicAdd(counts + h0 + hl, (unsigned long long)c);
+            }
+        }
+        __syncwarp();  // everybody has read its parked results: the row is free for the exchange
+
+        // ---- 2. bits over samples -> interleaved bits over (haplotype, strand) --------------------
+        transpose16x32_dev(a);
+
+        // ---- 3. exchange + expand + store ------------------------------------------------------------
+        {
+            uint32_t* dst = my_row + half * 16 + w;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) dst[m * 32] = a[m];
+        }
+        __syncthreads();  // the exchange is complete, and every warp is done with this half tile's records
+        const bool more = it + 1 < kHpc && ht + 1 < n_half;  // CTA-uniform
+        if (kStage && run_cnt && more) stage_run(ht + 1);  // the next run flies while this half is stored
+        hstore_phase(s_x, tid, n_blk_haps, ht, h0, n_samples, out, out_s_samp);
+        if (more) __syncthreads();  // the exchange rows are free for the next half's parked results
+    }
+}
+
 // evict_last policy word of the current device (made once per device and process; 0 = not made yet:
 // createpolicy never returns 0 for evict_last -- and if it did the word would just be made again)
 static int l2_policy(uint64_t* pol, cudaStream_t st) {
@@ -440,26 +463,29 @@ int launch_transform_u8_half(const uint32_t* planes, int64_t n_samples, int64_t 
                              const uint32_t* blk_key_lo, const uint32_t* blk_key_cnt, int64_t stage_lines) {
     uint64_t pol = 0;
     if (int rc = l2_policy(&pol, st)) return rc;
-    const int64_t n_half = (n_samples + kHalfSamples - 1) / kHalfSamples;
     const int64_t n_hb = (n_haps + kHapBlock - 1) / kHapBlock;
     const int64_t per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
     const bool stage = blk_key_lo && blk_key_cnt && stage_lines > 0;
+    // half tiles per CTA (HT_HALF_PER_CTA in the environment: measurements, tests)
+    const char* hpc_e = getenv("HT_HALF_PER_CTA");
+    const int hpc_env = hpc_e ? atoi(hpc_e) : 0;
+    const int hpc = (hpc_env ? hpc_env : kHalfPerCta) >= 2 ? 2 : 1;
+    const int64_t n_half = ((n_samples + kHalfSamples - 1) / kHalfSamples + hpc - 1) / hpc;  // groups of hpc half tiles
     const size_t smem = stage ? (size_t)stage_lines * 128 : 0;
-    if (stage)  // per launch: the attribute is per device, and a caller may drive several devices from one thread
-        HT_CUDA_TRY(cudaFuncSetAttribute(transform_u8_half_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int64_t t0 = 0; t0 < n_half; t0 += per_launch) {
-        const int64_t nt = min(per_launch, n_half - t0);
-        if (stage)
-            transform_u8_half_kernel<true><<<dim3((unsigned)(nt * n_hb)), kThreads, smem, st>>>(
-                planes, n_samples, n_keys, quad_off16, quads, blk_key_lo, blk_key_cnt, (uint32_t)stage_lines, n_haps,
-                (uint32_t)n_hb, t0, out, out_s_samp, counts, pol);
-        else
-            transform_u8_half_kernel<false><<<dim3((unsigned)(nt * n_hb)), kThreads, 0, st>>>(
-                planes, n_samples, n_keys, quad_off16, quads, nullptr, nullptr, 0u, n_haps, (uint32_t)n_hb, t0, out,
-                out_s_samp, counts, pol);
-        HT_CUDA_TRY(cudaGetLastError());
-    }
-    return HT_OK;
+    auto launch = [&](auto kernel) -> int {
+        if (stage)  // per launch: the attribute is per device, and a caller may drive several devices from one thread
+            HT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int64_t t0 = 0; t0 < n_half; t0 += per_launch) {
+            const int64_t nt = min(per_launch, n_half - t0);
+            kernel<<<dim3((unsigned)(nt * n_hb)), kThreads, smem, st>>>(
+                planes, n_samples, n_keys, quad_off16, quads, stage ? blk_key_lo : nullptr, stage ? blk_key_cnt : nullptr,
+                stage ? (uint32_t)stage_lines : 0u, n_haps, (uint32_t)n_hb, t0, out, out_s_samp, counts, pol);
+            HT_CUDA_TRY(cudaGetLastError());
+        }
+        return HT_OK;
+    };
+    if (stage) return hpc == 2 ? launch(transform_u8_half_kernel<true, 2>) : launch(transform_u8_half_kernel<true, 1>);
+    return hpc == 2 ? launch(transform_u8_half_kernel<false, 2>) : launch(transform_u8_half_kernel<false, 1>);
 }
 
 }  // namespace ht

@@ -39,7 +39,8 @@ for sort in (True, False):
     planes.random_(-(2**31), 2**31 - 1)
     lo, cnt = plan.block_spans()
     ref = None
-    for lines in ([0, 224, 256, 288, 352, 608] if sort else [0]):
+    for lines, hpc in ([(0, 1), (0, 2), (256, 1), (256, 2), (288, 2), (352, 2)] if sort else [(0, 1), (0, 2)]):
+        os.environ["HT_HALF_PER_CTA"] = str(hpc)
         dplan = engine.DevicePlan(plan, dev)
         dplan.stage_lines = lines
         if lines:
@@ -50,7 +51,7 @@ for sort in (True, False):
         chk = int(out[:4096].sum().item()) + int(out[-4096:].sum().item())
         ref = chk if ref is None else ref
         ab = plan.algorithmic_bytes(n)["transform"]
-        key = f"{'sorted' if sort else 'unsorted'} stage_lines={lines}"
+        key = f"{'sorted' if sort else 'unsorted'} stage_lines={lines} half_tiles_per_cta={hpc}"
         res[key] = {"ms": ms, "GBps": ab / ms / 1e6, "frac_of_6531": ab / ms / 1e6 / 6531.3, "same_result": chk == ref,
                     "staged_block_fraction": float(((cnt > 0) & (cnt <= lines)).mean()) if lines else 0.0,
                     "ms_at_500k": ms * 500_000 / n}

@@ -45,10 +45,11 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["half", "tile"])
+@pytest.mark.parametrize("kernel", ["half", "half2", "tile"])
 @pytest.mark.parametrize("n,p,H,max_k,long_hap", SHAPES)
 def test_transform_kernel_forms_vs_oracle(monkeypatch, kernel, n, p, H, max_k, long_hap):
-    monkeypatch.setenv("HT_TRANSFORM_KERNEL", kernel)
+    monkeypatch.setenv("HT_TRANSFORM_KERNEL", kernel[:4])
+    monkeypatch.setenv("HT_HALF_PER_CTA", "2" if kernel == "half2" else "1")  # two half tiles per CTA
     rng = np.random.default_rng(1000 * n + H)
     gt, plan, want = _case(rng, n, p, H, max_k, long_hap)
     dplan = engine.DevicePlan(plan)

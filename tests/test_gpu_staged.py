@@ -74,9 +74,11 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("hpc", [1, 2])
 @pytest.mark.parametrize("stage_lines", [None, 32, 256, 1536])
 @pytest.mark.parametrize("n,p,H,max_k,window,empty_every,wild_every", SHAPES)
-def test_staged_vs_oracle(n, p, H, max_k, window, empty_every, wild_every, stage_lines):
+def test_staged_vs_oracle(monkeypatch, n, p, H, max_k, window, empty_every, wild_every, stage_lines, hpc):
+    monkeypatch.setenv("HT_HALF_PER_CTA", str(hpc))  # half tiles per CTA (csrc/ht_transform_half.cu)
     rng = np.random.default_rng(31 * n + H)
     gt, plan, want = _local_case(rng, n, p, H, max_k, window, empty_every, wild_every)
     got, counts, dplan = _run(gt, plan, stage_lines, counts=True, extra_pitch=32 if n % 2 else 0)
