@@ -370,8 +370,8 @@ def device_workload(c, w, H, n, sample_offset, steps, warmup, method_arg, keep=F
     anc_ptr = anc.data_ptr() if anc is not None else 0
     anc_strides = anc.stride() if anc is not None else (0, 0, 0)
 
-    if method_arg == "auto":
-        method = "staged" if dplan.stage_lines > 0 else ("local" if dplan.use_local() else "direct")
+    if method_arg == "auto":  # what engine.transform_u8(method="auto") runs
+        method = "staged" if (engine.STAGED_AUTO and dplan.stage_lines > 0) else ("local" if dplan.use_local() else "direct")
     else:
         method = method_arg
     if method == "staged" and dplan.stage_lines == 0:
@@ -402,7 +402,7 @@ def device_workload(c, w, H, n, sample_offset, steps, warmup, method_arg, keep=F
     host_t1 = time.perf_counter()
     total_ms = c.max_over_ranks(t_begin.elapsed_time(t_end))
     r = {
-        "plan": plan, "dplan": dplan, "n": n, "n_requested": n_requested, "method": method,
+        "plan": plan, "dplan": dplan, "n": n, "n_requested": n_requested, "method": method, "sorted": bool(w.get("sort")),
         "ms_per_step": total_ms / K,
         "pack_ms": float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
         "tr_ms": float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
@@ -449,7 +449,10 @@ def roofline_of(r, peak, peak_src, kernel_env):
         kernel = "transform_u8_kernel"
     else:
         kernel = "transform_u8_half_kernel<true>" if r["method"] == "staged" else "transform_u8_half_kernel<false>"
-    traffic, traffic_src = measured_traffic(kernel, ab["transform"])
+    sorted_key = kernel + " (position-sorted haplotypes)"
+    traffic, traffic_src = measured_traffic(sorted_key if r.get("sorted") else kernel, ab["transform"])
+    if traffic is None and r.get("sorted"):
+        traffic, traffic_src = measured_traffic(kernel, ab["transform"])
     step_ms = r["ms_per_step"]
     return {
         "bound": "hbm", "kernel": kernel, "achieved": tr_gbs, "peak": peak, "unit": "GB/s", "frac": tr_gbs / peak,
@@ -849,10 +852,19 @@ def run_b200(args):
         rs = device_workload(c, ws, H, n, sample_offset, 5, 3, args.method)
         others["ukb_sorted"] = short_summary(rs, H, peak)
         others["ukb_sorted"]["note"] = ("the same plan with the haplotypes in position order -- what a .hap file is after `haptools index` "
-                                        "(haptools/index.py:31-94); blocks of 128 haplotypes then share a short run of keys and the transform "
-                                        f"stages it in shared memory (stage budget {rs['dplan'].stage_lines} lines)")
+                                        "(haptools/index.py:31-94); neighbouring haplotypes share plane records, which the half-tile kernel "
+                                        "picks up as L1 hits")
         gpu_launches += rs["launches_per_step"] * 5
         del rs
+        torch.cuda.empty_cache()
+        rst = device_workload(c, ws, H, n, sample_offset, 3, 3, "staged")
+        others["ukb_sorted"]["staged_form"] = {
+            "transform_ms": rst["tr_ms"], "transform_frac": rst["plan"].algorithmic_bytes(rst["n"])["transform"] / (rst["tr_ms"] * 1e-3) / 1e9 / peak,
+            "verified_against_oracle": rst["verified"], "stage_lines": rst["dplan"].stage_lines,
+            "note": "ht_transform_u8_staged (key runs of the haplotype blocks in shared memory): bit-exact, 2.1 x instead of 3.1 x the plane "
+                    "bytes from L2, not faster -- method='auto' does not pick it (engine.STAGED_AUTO)"}
+        gpu_launches += rst["launches_per_step"] * 3
+        del rst
         torch.cuda.empty_cache()
         for name in ("1000g", "ancestry"):
             wo = dict(WORKLOADS[name], sort=False)

@@ -34,6 +34,11 @@ LOCAL_AUTO = False
 # transform_host(result="auto"): results of this many bytes or more leave the device bit-packed and are widened
 # by the host copy engine; smaller ones as bytes (one DMA, no extra kernel, no hand-off to the pool)
 RESULT_BITS_MIN = 8 << 20
+# The shared-memory staged transform (ht_transform_u8_staged) is bit-exact and cuts the L2 -> SM record reads of
+# position-sorted haplotype sets from 3.1 x to 2.1 x the plane bytes, but on B200 it is SLOWER than the plain
+# half-tile kernel on those very sets (8.6 vs 8.2 ms at 200 k samples: 3 instead of 4 CTAs per SM and a CTA-wide
+# wait for the staged run): method="auto" keeps to the plain kernel unless this is set.
+STAGED_AUTO = False
 
 
 def require_cuda() -> None:
@@ -193,13 +198,13 @@ def transform_u8(dplan: DevicePlan, planes: torch.Tensor, n_samples: int, out_pt
             "staged": the same kernel with the key runs of its haplotype blocks staged in shared memory
             (ht_transform_u8_staged; pays for position-sorted haplotype sets, DevicePlan.stage_lines);
             "local": two phases through shared memory and a bit-packed intermediate
-            (ht_transform_u8_local); "auto": staged when the plan's blocks are key-local, else direct
-            (or local when LOCAL_AUTO is switched on).  Results are identical.
+            (ht_transform_u8_local); "auto": direct -- the other two are bit-exact but measured slower on
+            B200 (STAGED_AUTO / LOCAL_AUTO switch them on for plans they suit).  Results are identical.
     use_quads  False: let the kernel build its padded key quads from the CSR itself (the form
             without planner support; kept for callers that only have hap_off / hap_key)."""
     if method not in ("auto", "direct", "local", "staged"):
         raise ValueError("method must be 'auto', 'direct', 'staged' or 'local'")
-    if (method == "staged" or method == "auto") and use_quads and dplan.stage_lines > 0:
+    if (method == "staged" or (method == "auto" and STAGED_AUTO)) and use_quads and dplan.stage_lines > 0:
         check(
             _cuda.lib().ht_transform_u8_staged(
                 _ptr(planes), n_samples, dplan.n_keys, _ptr(dplan.hap_off), _ptr(dplan.hap_key),

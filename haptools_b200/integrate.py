@@ -78,26 +78,65 @@ def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
     if hap_gts is None:
         hap_gts = genotypes_vcf(fname=None, log=haps_obj.log)
     hap_gts.samples = gts.samples
-    hap_gts.variants = _result_variants(haps_obj, haps, hap_gts.variants.dtype)
+    # hap_gts.variants (O(H) string conversions, 30 ms at 100 k haplotypes) is built by a helper thread while this
+    # one drives the device: transform_host spends its time inside the library with the GIL released
+    variants_job = _Background(_result_variants, haps_obj, haps, hap_gts.variants.dtype)
     # the five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order (the first
     # two are emitted by the planner at the steps they belong to)
     log = haps_obj.log
-    plan = _cached_plan(haps_obj, haps, gts, ancestry, log)
+    try:
+        plan = _cached_plan(haps_obj, haps, gts, ancestry, log)
+    except BaseException:
+        hap_gts.variants = variants_job.result()  # the reference sets `variants` before it can fail (haplotypes.py:1369)
+        raise
     log.info(f"Transforming genotypes for {len(haps)} haplotypes")
     log.debug(
         f"Allocating array with dtype {gts.data.dtype} and size "
         f"{(len(gts.samples), len(haps), 2)}"
     )
     log.debug("Computing haplotype genotypes. This may take a while")
-    if ancestry and gts.data.shape[2] != 2:
-        # haptools/transform.py:137 compares the whole last axis; a leftover phase column
-        # makes the reference fail with a broadcast error -- same exception class here
-        raise ValueError(
-            f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
-            f"into shape {(gts.data.shape[0], 2)}"
-        )
-    hap_gts.data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
+    try:
+        if ancestry and gts.data.shape[2] != 2:
+            # haptools/transform.py:137 compares the whole last axis; a leftover phase column
+            # makes the reference fail with a broadcast error -- same exception class here
+            raise ValueError(
+                f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
+                f"into shape {(gts.data.shape[0], 2)}"
+            )
+        data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
+    finally:
+        hap_gts.variants = variants_job.result()
+    hap_gts.data = data
     return hap_gts
+
+
+class _Background:
+    """fn(*args) on a helper thread (inline for small jobs); result() joins and re-raises."""
+
+    def __init__(self, fn, haps_obj, haps, dtype):
+        import threading
+
+        self._out = self._err = self._thread = None
+
+        def run():
+            try:
+                self._out = fn(haps_obj, haps, dtype)
+            except BaseException as e:  # handed to the caller's thread
+                self._err = e
+
+        if len(haps) < 4096:
+            run()
+        else:
+            self._thread = threading.Thread(target=run, name="haptools_b200-variants", daemon=True)
+            self._thread.start()
+
+    def result(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        if self._err is not None:
+            raise self._err
+        return self._out
 
 
 # ----------------------------------------------------------------------------------------
