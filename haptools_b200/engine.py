@@ -674,6 +674,28 @@ class _HostPipe:
             self.cur.wait_stream(self.s_out)
 
 
+def download_result(buf: torch.Tensor, n: int, H: int, pitch: int, stream=None) -> np.ndarray:
+    """A device result `(n, pitch)` uint8 (0/1 bytes, 2H used per row) -> a host `(n, H, 2)` uint8 array, by host
+    copy engine jobs of at most 256 MB each (page-locked slots, several host threads, asynchronous DMA) -- all
+    submitted at once, so the blocks of one job overlap the staging of the others."""
+    lib = _cuda.lib()
+    out = _result_array((n, H, 2))
+    if n == 0 or H == 0:
+        return out
+    st = (stream or torch.cuda.current_stream(buf.device)).cuda_stream
+    if 2 * H > (8 << 20) or not _pageable(out.ctypes.data, out.nbytes):
+        _copy2d(out.ctypes.data, 2 * H, buf.data_ptr(), pitch, 2 * H, n, _cuda.HT_COPY_D2H, stream or torch.cuda.current_stream(buf.device))
+        (stream or torch.cuda.current_stream(buf.device)).synchronize()
+        return out
+    rows = max(1, (256 << 20) // max(2 * H, 1))
+    tickets = [_submit(lib.ht_host_submit_download(out.ctypes.data + s0 * 2 * H, 2 * H, buf.data_ptr() + s0 * pitch, pitch,
+                                                   2 * H, min(rows, n - s0), st), "ht_host_submit_download")
+               for s0 in range(0, n, rows)]
+    for t in tickets:
+        _host_wait(t)
+    return out
+
+
 def _gatherable(a: np.ndarray, plan: TransformPlan) -> bool:
     """Variant-major host array (a variant is a contiguous row of at most 8 MB) of which the plan refers to at
     most half the variants: only the referenced rows need to be uploaded."""

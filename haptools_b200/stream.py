@@ -178,14 +178,7 @@ def transform_pgen_stream(reader, variant_idxs: np.ndarray, n_samples: int, plan
             if fmt == "bits":
                 res = res.cpu().numpy().view(np.uint32)
             else:
-                host_out = np.empty((n, H, 2), dtype=np.uint8)
-                rows = max(1, (256 << 20) // max(2 * H, 1))
-                for s0 in range(0, n, rows):
-                    m = min(rows, n - s0)
-                    check(lib.ht_copy2d(host_out.ctypes.data + s0 * 2 * H, 2 * H, buf.data_ptr() + s0 * pitch, pitch,
-                                        2 * H, m, _cuda.HT_COPY_D2H, cur.cuda_stream), "ht_copy2d")
-                cur.synchronize()
-                res = host_out.view(np.bool_)
+                res = engine.download_result(buf, n, H, pitch, cur).view(np.bool_)
         if stats is not None:
             stats.update(h2d_s=sum(a.elapsed_time(b) for a, b, _, _ in ev_pairs) * 1e-3,
                          pack_s=sum(c.elapsed_time(d) for _, _, c, d in ev_pairs) * 1e-3)
