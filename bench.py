@@ -448,7 +448,7 @@ def roofline_of(r, peak, peak_src, kernel_env):
     elif kernel_env[:1] == "t":
         kernel = "transform_u8_kernel"
     else:
-        kernel = "transform_u8_half_kernel<true>" if r["method"] == "staged" else "transform_u8_half_kernel<false>"
+        kernel = "transform_u8_half_kernel<true, 1>" if r["method"] == "staged" else "transform_u8_half_kernel<false, 1>"
     sorted_key = kernel + " (position-sorted haplotypes)"
     traffic, traffic_src = measured_traffic(sorted_key if r.get("sorted") else kernel, ab["transform"])
     if traffic is None and r.get("sorted"):

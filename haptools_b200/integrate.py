@@ -74,7 +74,11 @@ def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
     from .plan import plan_from_haplotypes
 
     haps_obj.index()
-    haps = [haps_obj.data[hap] for hap in haps_obj.type_ids["H"]]
+    ids = haps_obj.type_ids["H"]
+    if len(ids) == len(haps_obj.data) and list(haps_obj.data) == ids:
+        haps = list(haps_obj.data.values())  # only haplotypes, in index order: no 100 k dict look-ups
+    else:
+        haps = list(map(haps_obj.data.__getitem__, ids))
     if hap_gts is None:
         hap_gts = genotypes_vcf(fname=None, log=haps_obj.log)
     hap_gts.samples = gts.samples
