@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override the cohort's samples (per GPU with --scaling weak)")
     ap.add_argument("--haps", type=int, default=0, help="override the number of haplotypes")
     ap.add_argument("--e2e-samples", type=int, default=0,
-                    help="samples of the host-buffer end-to-end legs over all ranks (default 65,536, capped by the shard)")
+                    help="samples of the host-buffer end-to-end legs over all ranks (default 65,536 PER RANK, capped by free host memory)")
     ap.add_argument("--cpu-samples", type=int, default=0,
                     help="samples of the CPU sample (default: 8192 for the cpu_baseline leg, in slices of 2048; 512 per process and step for --impl reference)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes of --impl reference (0 = all cores, max 16)")
@@ -280,13 +280,16 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
     return "not bound"
 
 
+TRANSFORM_SOURCES = ("ht_transform_half.cu", "ht_transform.cuh", "ht_common.cuh")
+
+
 def csrc_hash() -> str:
-    """Identity of the kernel sources a committed ncu capture belongs to."""
+    """Identity of the sources of the kernel the roofline is reported for (the half-tile transform): the committed
+    ncu capture in profiles/r2/traffic.json belongs to exactly these files."""
     h = hashlib.sha256()
-    for f in sorted((REPO / "haptools_b200" / "csrc").glob("*")):
-        if f.suffix in (".cu", ".cuh", ".cpp"):
-            h.update(f.name.encode())
-            h.update(f.read_bytes())
+    for name in TRANSFORM_SOURCES:
+        h.update(name.encode())
+        h.update((REPO / "haptools_b200" / "csrc" / name).read_bytes())
     return h.hexdigest()[:16]
 
 
@@ -605,8 +608,17 @@ def e2e_legs(c, w, H, args, n_shard, sample_offset):
     from haptools_b200.plan import plan_from_haplotypes
 
     p = w["p"]
-    total = args.e2e_samples or 65_536
-    ne = int(min(max(1024, total // c.world // 1024 * 1024), n_shard))
+    # every rank transforms its own batch at the same time (the e2e legs scale weakly: a caller with N GPUs brings N
+    # batches); the batch is capped by what the host has free: page-locked + pageable input, the result twice
+    per_sample = (2 * p * (2 if w["n_pops"] else 1)) * 2 + 2 * H * 3
+    try:
+        import psutil
+
+        fit = int(psutil.virtual_memory().available * 0.45 / c.world / per_sample)
+    except Exception:
+        fit = 16_384
+    want = args.e2e_samples // c.world if args.e2e_samples else 65_536
+    ne = int(min(max(1024, min(want, fit) // 1024 * 1024), n_shard if c.world == 1 else max(n_shard, 1024)))
     t0 = time.perf_counter()
     haps, gts = synth.synth_objects(p, H, w["seed"], n_pops=w["n_pops"], sort=w.get("sort", False))
     objects_s = time.perf_counter() - t0
@@ -693,7 +705,8 @@ def e2e_legs(c, w, H, args, n_shard, sample_offset):
            "numpy result allocated by the call); plan cache warm (identity-validated, integrate.py); all ranks concurrently, max time over ranks")
     e2e = {
         "value": calls / warm_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h_bits) * c.world,
-        "ms": warm_s * 1e3, "samples_per_gpu": ne, "api": api + "; gts.data page-locked",
+        "ms": warm_s * 1e3, "samples_per_gpu": ne, "e2e_scaling": "weak (every rank its own batch of samples_per_gpu samples, all at once)",
+        "api": api + "; gts.data page-locked",
         "planner_ms": planner_ms, "first_call_ms": cold_ms, "first_call_value": calls / (cold_ms * 1e-3),
         "api_overhead_ms": max(0.0, (warm_s - engine_s) * 1e3),
         "api_overhead_note": "class-API call minus the engine-level call: O(H) Python bookkeeping independent of the sample count "

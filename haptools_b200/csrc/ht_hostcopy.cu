@@ -3,7 +3,7 @@
 // of haptools/data/haplotypes.py:1408 is) and the device through page-locked staging slots, and that widens the
 // bit-packed result to the reference's bool bytes on the way down (ht_expand_host.cpp).
 //
-//   * one pool per process, started on first use (HT_HOST_COPY_THREADS workers, default min(cores, 12)); every
+//   * one pool per process, started on first use (HT_HOST_COPY_THREADS workers, default min(cores / ranks on this host, 12)); every
 //     worker owns two page-locked slots and one copy stream per device, so a worker always has one DMA in flight
 //     while it copies / expands the previous block
 //   * a job = one call (upload, download, download + expand) cut into row blocks; workers take blocks of the
@@ -136,7 +136,15 @@ class Pool {
         const char* e = getenv("HT_HOST_COPY_THREADS");
         int v = e ? atoi(e) : 0;
         const int hw = (int)std::thread::hardware_concurrency();
-        if (v <= 0) v = hw > 0 ? (hw < 12 ? hw : 12) : 4;
+        if (v <= 0) {
+            // default: min(cores, 12), shared fairly when a launcher runs one process per GPU on this host
+            // (torchrun exports LOCAL_WORLD_SIZE): 8 ranks x 12 workers on 32 cores only fight each other
+            const char* lws = getenv("LOCAL_WORLD_SIZE");
+            const int ranks = lws ? atoi(lws) : 1;
+            int share = hw > 0 ? hw / (ranks > 0 ? ranks : 1) : 4;
+            if (share < 3) share = 3;
+            v = share < 12 ? share : 12;
+        }
         if (hw > 0 && v > hw) v = hw;
         n_workers_ = v < 1 ? 1 : (v > kMaxWorkers ? kMaxWorkers : v);
     }
