@@ -69,69 +69,98 @@ def haplotype_ancestry_transform(hap, genotypes) -> np.ndarray:
 def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
     """Body of ``Haplotypes.transform`` (haptools/data/haplotypes.py:1339-1413) and, with ``ancestry=True``, of
     ``HaplotypesAncestry.transform`` (haptools/transform.py:91-149).  ``genotypes_vcf``: the GenotypesVCF class
-    to instantiate when ``hap_gts`` is None (the reference's own when installed on the reference)."""
-    from . import engine
-    from .plan import plan_from_haplotypes
+    to instantiate when ``hap_gts`` is None (the reference's own when installed on the reference).
 
+    Everything that is O(H) Python -- the list of haplotypes, the identity check of the cached plan, the result's
+    ``variants`` array: 80 ms at 100 k haplotypes -- runs on a helper thread while this one drives the device
+    (``transform_host`` spends its time inside the library with the GIL released).  A cached plan is therefore used
+    OPTIMISTICALLY: the device starts on it at once, and if the helper finds that something the plan was built from
+    has been replaced since, the result is dropped and the call starts over with a fresh plan."""
     haps_obj.index()
-    ids = haps_obj.type_ids["H"]
-    if len(ids) == len(haps_obj.data) and list(haps_obj.data) == ids:
-        haps = list(haps_obj.data.values())  # only haplotypes, in index order: no 100 k dict look-ups
-    else:
-        haps = list(map(haps_obj.data.__getitem__, ids))
     if hap_gts is None:
         hap_gts = genotypes_vcf(fname=None, log=haps_obj.log)
     hap_gts.samples = gts.samples
-    # hap_gts.variants (O(H) string conversions, 30 ms at 100 k haplotypes) is built by a helper thread while this
-    # one drives the device: transform_host spends its time inside the library with the GIL released
-    variants_job = _Background(_result_variants, haps_obj, haps, hap_gts.variants.dtype)
-    # the five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order (the first
-    # two are emitted by the planner at the steps they belong to)
-    log = haps_obj.log
-    try:
-        plan = _cached_plan(haps_obj, haps, gts, ancestry, log)
-    except BaseException:
-        hap_gts.variants = variants_job.result()  # the reference sets `variants` before it can fail (haplotypes.py:1369)
-        raise
-    log.info(f"Transforming genotypes for {len(haps)} haplotypes")
-    log.debug(
-        f"Allocating array with dtype {gts.data.dtype} and size "
-        f"{(len(gts.samples), len(haps), 2)}"
-    )
-    log.debug("Computing haplotype genotypes. This may take a while")
-    try:
-        if ancestry and gts.data.shape[2] != 2:
-            # haptools/transform.py:137 compares the whole last axis; a leftover phase column
-            # makes the reference fail with a broadcast error -- same exception class here
-            raise ValueError(
-                f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
-                f"into shape {(gts.data.shape[0], 2)}"
-            )
-        data = engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
-    finally:
-        hap_gts.variants = variants_job.result()
+    n_haps = len(haps_obj.type_ids["H"])
+    entry = _cache_probe(haps_obj, gts, ancestry, n_haps)
+    if entry is not None:
+        job = _Background(_list_check_variants, n_haps, haps_obj, entry, ancestry, hap_gts.variants.dtype)
+        plan, n_distinct = entry[2], entry[3]
+        with _ShortSwitchInterval(job.threaded):
+            try:
+                data = _logged_transform(haps_obj.log, gts, plan, n_haps, ancestry, n_distinct)
+            except BaseException:
+                hap_gts.variants = job.result()[2]
+                raise
+            haps, fresh, variants = job.result()
+        if fresh:
+            hap_gts.variants, hap_gts.data = variants, data
+            return hap_gts
+        del data  # built from a plan that no longer describes these haplotypes
+        clear_plan_cache(haps_obj)
+    else:
+        haps = _haplotype_list(haps_obj)
+    job = _Background(_result_variants, len(haps), haps_obj, haps, hap_gts.variants.dtype)
+    with _ShortSwitchInterval(job.threaded):
+        try:
+            # the planner emits the first two of the five log lines at the steps they belong to
+            plan = _planned(haps_obj, haps, gts, ancestry, haps_obj.log)
+            data = _logged_transform(haps_obj.log, gts, plan, len(haps), ancestry, None)
+        finally:
+            hap_gts.variants = job.result()  # the reference sets `variants` before it can fail (haplotypes.py:1369)
     hap_gts.data = data
     return hap_gts
 
 
-class _Background:
-    """fn(*args) on a helper thread (inline for small jobs); result() joins and re-raises."""
+def _haplotype_list(haps_obj) -> list:
+    ids = haps_obj.type_ids["H"]
+    if len(ids) == len(haps_obj.data) and list(haps_obj.data) == ids:
+        return list(haps_obj.data.values())  # only haplotypes, in index order: no 100 k dict look-ups
+    return list(map(haps_obj.data.__getitem__, ids))
 
-    def __init__(self, fn, haps_obj, haps, dtype):
+
+def _logged_transform(log, gts, plan, n_haps, ancestry, n_distinct):
+    """The five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order, around the
+    library call (``n_distinct`` None: the planner has just emitted the first two)."""
+    from . import engine
+
+    if n_distinct is not None:
+        log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
+        log.debug("Creating array denoting alt allele status")
+    log.info(f"Transforming genotypes for {n_haps} haplotypes")
+    log.debug(
+        f"Allocating array with dtype {gts.data.dtype} and size "
+        f"{(len(gts.samples), n_haps, 2)}"
+    )
+    log.debug("Computing haplotype genotypes. This may take a while")
+    if ancestry and gts.data.shape[2] != 2:
+        # haptools/transform.py:137 compares the whole last axis; a leftover phase column
+        # makes the reference fail with a broadcast error -- same exception class here
+        raise ValueError(
+            f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
+            f"into shape {(gts.data.shape[0], 2)}"
+        )
+    return engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
+
+
+class _Background:
+    """fn(*args) on a helper thread (inline when ``size`` is small); result() joins and re-raises."""
+
+    def __init__(self, fn, size, *args):
         import threading
 
         self._out = self._err = self._thread = None
 
         def run():
             try:
-                self._out = fn(haps_obj, haps, dtype)
+                self._out = fn(*args)
             except BaseException as e:  # handed to the caller's thread
                 self._err = e
 
-        if len(haps) < 4096:
+        self.threaded = size >= 4096
+        if not self.threaded:
             run()
         else:
-            self._thread = threading.Thread(target=run, name="haptools_b200-variants", daemon=True)
+            self._thread = threading.Thread(target=run, name="haptools_b200-helper", daemon=True)
             self._thread.start()
 
     def result(self):
@@ -143,6 +172,30 @@ class _Background:
         return self._out
 
 
+class _ShortSwitchInterval:
+    """While a helper thread runs Python next to the thread that drives the device, the driving thread has to win
+    the GIL back after every library call; with the interpreter's default switch interval (5 ms) each of the
+    ~100 calls of a transform could wait that long.  0.2 ms for the duration of the call, then the old value."""
+
+    def __init__(self, active: bool):
+        self._active, self._old = active, None
+
+    def __enter__(self):
+        import sys
+
+        if self._active:
+            self._old = sys.getswitchinterval()
+            sys.setswitchinterval(min(self._old, 2e-4))
+        return self
+
+    def __exit__(self, *exc):
+        import sys
+
+        if self._old is not None:
+            sys.setswitchinterval(self._old)
+        return False
+
+
 # ----------------------------------------------------------------------------------------
 # plan cache
 # ----------------------------------------------------------------------------------------
@@ -152,7 +205,10 @@ class _Background:
 # `haptools transform` on chunked input and `haptools ld` do -- get the plan of the previous call back when
 # nothing it was built from has been replaced: the `data` dict and `type_ids` of the Haplotypes object, the
 # `variants` TUPLE of every haplotype (tuples are immutable; the check is by identity, O(H)), the `variants`
-# array and ID index of the genotypes, the dtype class of `data` and the ancestry label dict.  What the check
+# array and ID index of the genotypes, the dtype class of `data` and the ancestry label dict.  The O(1) part of
+# that stamp decides whether the entry is tried at all (`_cache_probe`); the O(H) part runs on the helper thread
+# NEXT TO the transform that already uses the plan (`_list_check_variants`), and a transform whose plan turns out
+# stale is thrown away and repeated with a fresh plan (tests/test_plan_cache.py).  What the check
 # cannot see is an IN-PLACE edit of a Variant's fields or of the genotypes' `variants` array between two calls;
 # code that does that sets HAPTOOLS_B200_PLAN_CACHE=0 (or calls clear_plan_cache(haps)).
 _CACHE_ATTR = "_haptools_b200_plan_cache"
@@ -189,37 +245,54 @@ def _cache_enabled() -> bool:
     return os.environ.get("HAPTOOLS_B200_PLAN_CACHE", "1").strip() not in ("0", "off", "no")
 
 
-def _cached_plan(haps_obj, haps, gts, ancestry, log):
+def _stamp(haps_obj, gts, ancestry):
+    """The O(1) part of what a plan was built from (compared by identity up to index 2, by value after)."""
+    return (
+        haps_obj.data, gts.variants, gts._var_idx, gts.data.dtype == np.bool_, gts.data.shape[1], bool(ancestry),
+        tuple(sorted(gts.ancestry_labels.items())) if ancestry else None,
+    )
+
+
+def _cache_probe(haps_obj, gts, ancestry, n_haps):
+    """The cache entry if its O(1) stamp matches this call (the O(H) part is `_list_check_variants`), else None."""
+    if not _cache_enabled():
+        return None
+    entry = haps_obj.__dict__.get(_CACHE_ATTR)
+    if entry is None:
+        return None
+    gts.index(samples=False, variants=True)  # raises on duplicate IDs like the planner would
+    old, new = entry[0], _stamp(haps_obj, gts, ancestry)
+    if old[0] is new[0] and old[1] is new[1] and old[2] is new[2] and old[3:] == new[3:] and len(entry[1]) == n_haps:
+        return entry
+    return None
+
+
+def _list_check_variants(haps_obj, entry, ancestry, dtype):
+    """Helper-thread half of a call that found a cache entry: (haplotype list, entry still valid, `variants`)."""
     from operator import is_
 
+    haps = _haplotype_list(haps_obj)
+    tuples = [h.variants for h in haps]
+    fresh = len(tuples) == len(entry[1]) and all(map(is_, entry[1], tuples))
+    if fresh and ancestry:
+        fresh = [h.ancestry for h in haps] == entry[4]
+    return haps, fresh, _result_variants(haps_obj, haps, dtype)
+
+
+def _planned(haps_obj, haps, gts, ancestry, log):
+    """A fresh plan, remembered for the next call (unless the cache is switched off)."""
     from .plan import plan_from_haplotypes
 
     if not _cache_enabled():
         return plan_from_haplotypes(haps, gts, ancestry=ancestry, log=log)
     gts.index(samples=False, variants=True)  # raises on duplicate IDs like the planner would
-    tuples = [h.variants for h in haps]
-    stamp = (
-        haps_obj.data, gts.variants, gts._var_idx, gts.data.dtype == np.bool_, gts.data.shape[1], bool(ancestry),
-        tuple(sorted(gts.ancestry_labels.items())) if ancestry else None,
-        [h.ancestry for h in haps] if ancestry else None,
-    )
-    entry = haps_obj.__dict__.get(_CACHE_ATTR)
-    if entry is not None:
-        old_stamp, old_tuples, plan, n_distinct = entry
-        same = (
-            old_stamp[0] is stamp[0] and old_stamp[1] is stamp[1] and old_stamp[2] is stamp[2]
-            and old_stamp[3:] == stamp[3:] and len(old_tuples) == len(tuples)
-            and all(map(is_, old_tuples, tuples))
-        )
-        if same:
-            # the planner's two debug lines (haplotypes.py:1387, 1389), as on the first call
-            log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
-            log.debug("Creating array denoting alt allele status")
-            return plan
     seen = []
     plan = plan_from_haplotypes(haps, gts, ancestry=ancestry, log=log, n_distinct_out=seen)
     # the entry keeps the tuples (and the two arrays) alive, so an `is` match can never be a recycled address
-    haps_obj.__dict__[_CACHE_ATTR] = (stamp, tuples, plan, seen[0])
+    haps_obj.__dict__[_CACHE_ATTR] = (
+        _stamp(haps_obj, gts, ancestry), [h.variants for h in haps], plan, seen[0],
+        [h.ancestry for h in haps] if ancestry else None,
+    )
     return plan
 
 
