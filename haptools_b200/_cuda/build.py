@@ -18,7 +18,7 @@ REPO = PKG.parent
 CSRC = PKG / "csrc"
 INCLUDE = REPO / "include"
 LIB_PATH = Path(__file__).resolve().parent / "libhaptools_cuda.so"
-SOURCES = ["ht_capi.cu", "ht_hostcopy.cu", "ht_expand_host.cpp", "ht_pack.cu", "ht_transform.cu", "ht_transform_half.cu", "ht_transform_local.cu", "ht_hapmajor.cu", "ht_synth.cu", "ht_breakpoints.cu", "ht_qc.cu"]
+SOURCES = ["ht_capi.cu", "ht_hostcopy.cu", "ht_expand_host.cpp", "ht_pack.cu", "ht_pack_anc_tma.cu", "ht_transform.cu", "ht_transform_half.cu", "ht_transform_local.cu", "ht_hapmajor.cu", "ht_synth.cu", "ht_breakpoints.cu", "ht_qc.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",

@@ -100,11 +100,14 @@ def test_both_forms_agree_at_size():
     assert int(outs[0][1].sum()) == int(outs[0][0].sum())
 
 
-@pytest.mark.parametrize("form", ["line", "warp"])
-@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1032, 40, 70), (2504, 64, 200), (3104, 200, 333), (1025, 1000, 400)])
+@pytest.mark.parametrize("form", ["tma", "line", "warp"])
+@pytest.mark.parametrize("n,p,H", [(40, 8, 5), (1032, 40, 70), (2504, 64, 200), (3104, 200, 333), (1025, 1000, 400),
+                                   (127, 72, 50), (129, 136, 90), (4000, 520, 700)])
 def test_ancestry_pack_forms_vs_oracle(monkeypatch, form, n, p, H):
-    """Both forms of the sample-major ancestry pack (csrc/ht_pack.cu: pack_sm2_anc_line_kernel, the default,
-    and pack_sm2_anc_kernel) against the oracle, with missing calls and labels >= 8 in the data."""
+    """The three forms of the sample-major ancestry pack (csrc/ht_pack_anc_tma.cu: pack_sm2_anc_tma_kernel, the
+    default; csrc/ht_pack.cu: pack_sm2_anc_line_kernel and pack_sm2_anc_kernel) against the oracle, with missing
+    calls and labels >= 8 in the data; sample counts around the 128-row slabs and column counts around the
+    64-column boxes of the TMA form."""
     monkeypatch.setenv("HT_PACK_ANC_KERNEL", form)
     from haptools_b200 import _cuda
 
