@@ -63,6 +63,7 @@ static bool is_pageable(const void* p) {
 // host memory, unified addressing) and write them to the device buffer -- no host thread touches a byte
 // and the call is asynchronous on the stream.  A warp per row, 16-byte loads, four in flight per lane.
 // ---------------------------------------------------------------------------------------
+template <int kUnroll>
 __global__ void __launch_bounds__(256) gather_rows_kernel(uint8_t* __restrict__ dst, int64_t dst_pitch,
                                                           const uint8_t* __restrict__ src, int64_t src_pitch,
                                                           int64_t width, const uint32_t* __restrict__ row_idx,
@@ -76,14 +77,22 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(uint8_t* __restrict__ 
         const uint4* s = reinterpret_cast<const uint4*>(srow);
         uint4* d = reinterpret_cast<uint4*>(drow);
         int64_t i = lane;
-        for (; i + 96 < n16; i += 128) {
-            const uint4 v0 = s[i], v1 = s[i + 32], v2 = s[i + 64], v3 = s[i + 96];
-            d[i] = v0;
-            d[i + 32] = v1;
-            d[i + 64] = v2;
-            d[i + 96] = v3;
+        for (; i + 32 * (kUnroll - 1) < n16; i += 32 * kUnroll) {
+            uint4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) v[u] = s[i + 32 * u];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) d[i + 32 * u] = v[u];
         }
-        for (; i < n16; i += 32) d[i] = s[i];
+        {  // the last, partial batch: still all of its loads before the first store
+            uint4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (i + 32 * u < n16) v[u] = s[i + 32 * u];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (i + 32 * u < n16) d[i + 32 * u] = v[u];
+        }
         const int64_t t0 = n16 << 4;  // the last width % 16 bytes
         if (t0 + lane < width) drow[t0 + lane] = srow[t0 + lane];
     }
@@ -109,8 +118,19 @@ static int gather_rows_from_pinned(void* dst, int64_t dst_pitch, const void* src
     cudaError_t e = cudaMemcpyAsync(d_idx, row_idx, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         const int64_t ctas = (n_rows + 7) / 8;
-        const unsigned grid = (unsigned)(ctas < 148 * 8 ? ctas : 148 * 8);
-        gather_rows_kernel<<<grid, 256, 0, st>>>(static_cast<uint8_t*>(dst), dst_pitch, dsrc, src_pitch, width, d_idx, n_rows);
+        const char* ce = getenv("HT_GATHER_CTAS");  // measurements
+        const char* ue = getenv("HT_GATHER_UNROLL");
+        const int64_t max_ctas = ce && atoi(ce) > 0 ? atoi(ce) : 148 * 8;
+        const unsigned grid = (unsigned)(ctas < max_ctas ? ctas : max_ctas);
+        // loads in flight per lane and the grid make no difference (48.0-48.8 GB/s for 4 / 8 / 16 loads and 148 to
+        // 2,368 CTAs against 55.6 GB/s for a DMA of the same bytes, profiles/r2/gather.json): the link's read
+        // protocol bounds SM-issued reads, not the kernel
+        if (ue && atoi(ue) == 8)
+            gather_rows_kernel<8><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(dst), dst_pitch, dsrc, src_pitch, width, d_idx, n_rows);
+        else if (ue && atoi(ue) == 16)
+            gather_rows_kernel<16><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(dst), dst_pitch, dsrc, src_pitch, width, d_idx, n_rows);
+        else
+            gather_rows_kernel<4><<<grid, 256, 0, st>>>(static_cast<uint8_t*>(dst), dst_pitch, dsrc, src_pitch, width, d_idx, n_rows);
         e = cudaGetLastError();
     }
     const cudaError_t ef = cudaFreeAsync(d_idx, st);
