@@ -204,12 +204,23 @@ pack_sm2_anc_tma_kernel(const __grid_constant__ CUtensorMap map_gt, const __grid
     auto key_info = [&](int key) {
         return (uint32_t)__ldg(a.key_allele + key) | ((uint32_t)__ldg(a.key_label + key) << 8);
     };
+    // the prefetched bytes stay in the registers the loads fill (no arithmetic on them before phase B: the first
+    // instruction that touches a loaded byte waits for it)
+    auto fetch_info = [&](const int2& r, uint32_t (&al)[kInfoAhead], uint32_t (&lb)[kInfoAhead]) {
+#pragma unroll
+        for (int t = 0; t < kInfoAhead; ++t) {
+            al[t] = lb[t] = 0u;
+            if (t < r.y) {
+                al[t] = __ldg(a.key_allele + r.x + t);
+                lb[t] = __ldg(a.key_label + r.x + t);
+            }
+        }
+    };
     uint32_t k = group;
     TmaItem it = tma_item<Idx>(w, k);
     int2 kr = key_range(it);
-    uint32_t info[kInfoAhead];
-#pragma unroll
-    for (int t = 0; t < kInfoAhead; ++t) info[t] = t < kr.y ? key_info(kr.x + t) : 0u;
+    uint32_t info_a[kInfoAhead], info_l[kInfoAhead];
+    fetch_info(kr, info_a, info_l);
     uint32_t s = group % kTmaStages, round = group / kTmaStages;
 
     while (it.valid) {
@@ -311,14 +322,13 @@ pack_sm2_anc_tma_kernel(const __grid_constant__ CUtensorMap map_gt, const __grid
             };
 #pragma unroll
             for (int t = 0; t < kInfoAhead; ++t)
-                if (t < kr.y) emit(info[t], t);
+                if (t < kr.y) emit(info_a[t] | (info_l[t] << 8), t);
 #pragma unroll 1
             for (int t = kInfoAhead; t < kr.y; ++t) emit(key_info(kr.x + t), t);
         }
 
         // next item of my group
-#pragma unroll
-        for (int t = 0; t < kInfoAhead; ++t) info[t] = t < kr_next.y ? key_info(kr_next.x + t) : 0u;
+        fetch_info(kr_next, info_a, info_l);
         it = it_next;
         kr = kr_next;
         k += kTmaGroups;
