@@ -346,8 +346,12 @@ int64_t submit(int kind, void* dst, int64_t dst_pitch, const void* src, int64_t 
     job->out_width = out_width;
     if (row_idx) job->row_idx.assign(row_idx, row_idx + height);
     // block size: whole rows, at most a slot; small enough that every worker gets a few blocks of a big job
-    // (an expanded block writes 8 x its bytes, so those are cut finer)
-    const size_t target = kind == kDownloadExpand ? (1u << 20) : (4u << 20);
+    // (an expanded block writes 8 x its bytes, so those are cut finer: 512 KB of bits = 4 MB of result; 16,384 samples
+    // of the UKB plan end to end: 39.4 ms against 42.8 ms with 1 MB blocks and 48 ms with 128 KB; upload blocks
+    // below 4 MB only lose, 64.8 ms at 1 MB for a pageable source -- profiles/r2/host_blocks.json)
+    size_t target = kind == kDownloadExpand ? (512u << 10) : (4u << 20);
+    if (const char* e = getenv(kind == kDownloadExpand ? "HT_HOST_EXPAND_BLOCK_KB" : "HT_HOST_BLOCK_KB"))  // measurements
+        if (atol(e) > 0) target = (size_t)atol(e) << 10;
     int64_t rpb = (int64_t)(target / (size_t)width);
     const int64_t max_rpb = (int64_t)(kSlotBytes / (size_t)width);
     if (rpb < 1) rpb = 1;
