@@ -506,7 +506,6 @@ class _HostPipe:
         lib = _cuda.lib()
         with torch.cuda.device(dev):
             self.dplan = dplan if dplan is not None and dplan.device == dev else device_plan(plan, dev)
-            self.nbuf = nbuf = min(2, len(bounds))
             self.pitch = out_pitch(H)
             ends = sorted(bounds, key=lambda b: b[0] - b[1])[:2] + bounds[-1:]  # the largest chunks (and the last)
             # Variant-major host array (VCF reader layout: a variant is a contiguous row) of which the plan
@@ -527,22 +526,40 @@ class _HostPipe:
                 gt_bytes = max(plan.n_vars * _region(gt, *b).dev_pitch() for b in ends)
             else:
                 gt_bytes = max(_region(gt, *b).dev_bytes() for b in ends)
-            self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-            self.anc_buf = [None] * nbuf
+            anc_bytes = 0
             if plan.has_ancestry:
                 if self.gather:
                     anc_bytes = max(plan.n_vars * _region(ancestry, *b).dev_pitch() for b in ends)
                 else:
                     anc_bytes = max(_region(ancestry, *b).dev_bytes() for b in ends)
-                self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             if result == "bits":
                 self.bits_pitch = int(lib.ht_rowbits_pitch(H))
+                out_bytes = chunk * self.bits_pitch
+            else:
+                out_bytes = chunk * self.pitch
+            # Buffers per stage.  Two are what the DEVICE needs (upload k+1 || kernels k || download k-1).  More of
+            # them take the host waits out of the loop that queues the chunks: with a buffer set per chunk nothing
+            # is reused, so the one Python thread queues the whole call in a few ms and then sits in finish() with
+            # the GIL released -- whatever else runs in the interpreter (the class API's helper thread) no longer
+            # delays a chunk.  Bounded by a quarter of the free device memory (HAPTOOLS_B200_PIPE_DEPTH overrides).
+            depth = os.environ.get("HAPTOOLS_B200_PIPE_DEPTH", "").strip()
+            if depth:
+                want = max(2, int(depth))
+            else:
+                free = torch.cuda.mem_get_info(dev)[0]
+                want = max(2, int(free // 4 // max(gt_bytes + anc_bytes + out_bytes, 1)))
+            self.nbuf = nbuf = min(want, len(bounds))
+            self.queues_everything = nbuf >= len(bounds)
+            self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.anc_buf = [None] * nbuf
+            if plan.has_ancestry:
+                self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            if result == "bits":
                 tiles = (chunk + TILE - 1) // TILE
                 self.bits = torch.empty((tiles, H, 32, 2), dtype=torch.int32, device=dev)
-                self.out_buf = [torch.empty(chunk * self.bits_pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-            else:
-                self.out_buf = [torch.empty(chunk * self.pitch, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+            self.out_buf = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.out_pageable = _pageable(self.out_ptr, out.nbytes)
+            self.src_pageable = _pageable(r0.ptr, r0.width * r0.rows)  # its uploads are host copy engine jobs the loop waits for
             self.planes = alloc_planes(chunk, plan.n_keys, dev)
             self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             self.cur = torch.cuda.current_stream(dev)
@@ -722,7 +739,7 @@ def upload_bytes(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = Non
 def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = None, device=None,
                    chunk_samples: int = None, out: np.ndarray = None, pin_output: bool = None,
                    dplan: DevicePlan = None, pack_mode: int = _cuda.HT_PACK_AUTO, devices=None,
-                   result: str = "auto") -> np.ndarray:
+                   result: str = "auto", on_queued=None) -> np.ndarray:
     """
     gt (n, p, 2|3) uint8/bool host array (a view is fine: VCF-style transposed, PGEN-style
     with a phase column, C-contiguous ...) -> (n, H, 2) numpy bool, bit-identical to the
@@ -737,6 +754,8 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
              bandwidth becomes the bound); "u8": the bytes themselves (DMA into a page-locked array, through
              the engine's slots into a pageable one); "auto": "bits" for results of RESULT_BITS_MIN bytes or
              more (HAPTOOLS_B200_RESULT in the environment overrides).
+    on_queued  optional callable, invoked once from this thread at the point after which it only waits (GIL
+             released) for the device and the host copy engine: the class API starts its O(H) Python work there.
     """
     require_cuda()
     if gt.ndim != 3 or gt.shape[2] < 2 or gt.dtype not in (np.uint8, np.bool_):
@@ -786,8 +805,15 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
         raise ValueError("result must be 'auto', 'bits' or 'u8'")
     pipes = [_HostPipe(d, plan, dplan, gt, ancestry, bounds[i :: len(devs)], chunk, pack_mode, out, H, result)
              for i, d in enumerate(devs)]
+    # on_queued: called once, when this thread has no more than waiting left to do -- after the loop when every pipe
+    # holds a buffer set per chunk (nothing in the loop waits then), else before it (the loop is most of the call)
+    early = on_queued is not None and not all(pp.queues_everything and not pp.src_pageable for pp in pipes)
+    if early:
+        on_queued()
     for k in range(len(bounds)):
         pipes[k % len(pipes)].step()
+    if on_queued is not None and not early:
+        on_queued()
     for pipe in pipes:
         pipe.finish()
     return view

@@ -83,11 +83,13 @@ def haplotypes_transform(haps_obj, gts, hap_gts, ancestry: bool, genotypes_vcf):
     n_haps = len(haps_obj.type_ids["H"])
     entry = _cache_probe(haps_obj, gts, ancestry, n_haps)
     if entry is not None:
-        job = _Background(_list_check_variants, n_haps, haps_obj, entry, ancestry, hap_gts.variants.dtype)
+        # the helper starts when the engine has queued what it can queue without waiting (engine.transform_host
+        # `on_queued`): from then on this thread only waits inside the library, and the helper has the interpreter
+        job = _Background(_list_check_variants, n_haps, haps_obj, entry, ancestry, hap_gts.variants.dtype, defer=True)
         plan, n_distinct = entry[2], entry[3]
         with _ShortSwitchInterval(job.threaded):
             try:
-                data = _logged_transform(haps_obj.log, gts, plan, n_haps, ancestry, n_distinct)
+                data = _logged_transform(haps_obj.log, gts, plan, n_haps, ancestry, n_distinct, on_queued=job.start)
             except BaseException:
                 hap_gts.variants = job.result()[2]
                 raise
@@ -118,7 +120,7 @@ def _haplotype_list(haps_obj) -> list:
     return list(map(haps_obj.data.__getitem__, ids))
 
 
-def _logged_transform(log, gts, plan, n_haps, ancestry, n_distinct):
+def _logged_transform(log, gts, plan, n_haps, ancestry, n_distinct, on_queued=None):
     """The five log lines of haplotypes.py:1387-1410 / transform.py:122-143, verbatim and in order, around the
     library call (``n_distinct`` None: the planner has just emitted the first two)."""
     from . import engine
@@ -139,31 +141,43 @@ def _logged_transform(log, gts, plan, n_haps, ancestry, n_distinct):
             f"could not broadcast input array from shape {(gts.data.shape[0], gts.data.shape[2])} "
             f"into shape {(gts.data.shape[0], 2)}"
         )
-    return engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None)
+    kw = {"on_queued": on_queued} if on_queued is not None else {}
+    return engine.transform_host(gts.data, plan, ancestry=gts.ancestry if ancestry else None, **kw)
 
 
 class _Background:
-    """fn(*args) on a helper thread (inline when ``size`` is small); result() joins and re-raises."""
+    """fn(*args) on a helper thread (inline when ``size`` is small); result() joins and re-raises.  ``defer``: the
+    work begins at start() (or, if nobody called that, inside result())."""
 
-    def __init__(self, fn, size, *args):
+    def __init__(self, fn, size, *args, defer: bool = False):
+        self._out = self._err = self._thread = None
+        self._fn, self._args, self._started = fn, args, False
+        self.threaded = size >= 4096
+        if not defer:
+            self.start()
+
+    def _run(self):
+        try:
+            self._out = self._fn(*self._args)
+        except BaseException as e:  # handed to the caller's thread
+            self._err = e
+
+    def start(self):
         import threading
 
-        self._out = self._err = self._thread = None
-
-        def run():
-            try:
-                self._out = fn(*args)
-            except BaseException as e:  # handed to the caller's thread
-                self._err = e
-
-        self.threaded = size >= 4096
+        if self._started:
+            return
+        self._started = True
         if not self.threaded:
-            run()
+            self._run()
         else:
-            self._thread = threading.Thread(target=run, name="haptools_b200-helper", daemon=True)
+            self._thread = threading.Thread(target=self._run, name="haptools_b200-helper", daemon=True)
             self._thread.start()
 
     def result(self):
+        if not self._started:  # never started (the engine failed before it got there): do the work here
+            self.threaded = False
+            self.start()
         if self._thread is not None:
             self._thread.join()
             self._thread = None

@@ -180,3 +180,26 @@ def test_auto_picks_bits_for_large_results(monkeypatch):
     monkeypatch.setenv("HAPTOOLS_B200_RESULT", "u8")
     np.testing.assert_array_equal(engine.transform_host(gt, plan), want)
     assert not seen
+
+
+@pytest.mark.parametrize("result", ["u8", "bits"])
+@pytest.mark.parametrize("depth", ["2", "3", ""])
+def test_pipe_depth_and_on_queued(monkeypatch, depth, result):
+    """Buffer sets per stage of transform_host's pipeline: 2 (what the device needs; buffers are reused and the
+    queueing loop waits), 3, and the default (a set per chunk when device memory allows: nothing is reused and the
+    whole call is queued before the first wait) -- same result, and `on_queued` fires exactly once, with a
+    page-locked and with a pageable source."""
+    if depth:
+        monkeypatch.setenv("HAPTOOLS_B200_PIPE_DEPTH", depth)
+    else:
+        monkeypatch.delenv("HAPTOOLS_B200_PIPE_DEPTH", raising=False)
+    rng = np.random.default_rng(33)
+    n, p, H = 9_000, 700, 650
+    gt, anc, plan, want = _random_arrays(rng, n, p, H, max_k=4, missing=0.01, n_pops=5)
+    pinned_in, pinned_anc = engine.pinned_empty(gt.shape), engine.pinned_empty(anc.shape)
+    pinned_in[:], pinned_anc[:] = gt, anc
+    for g, a in ((pinned_in, pinned_anc), (gt, anc)):
+        fired = []
+        got = engine.transform_host(g, plan, ancestry=a, chunk_samples=1024, result=result, on_queued=lambda: fired.append(1))
+        np.testing.assert_array_equal(got, want)
+        assert fired == [1]
