@@ -548,16 +548,27 @@ class _HostPipe:
             else:
                 free = torch.cuda.mem_get_info(dev)[0]
                 want = max(2, int(free // 4 // max(gt_bytes + anc_bytes + out_bytes, 1)))
-            self.nbuf = nbuf = min(want, len(bounds))
+            nbuf = min(want, len(bounds))
+            while True:
+                try:
+                    self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+                    self.anc_buf = [None] * nbuf
+                    if plan.has_ancestry:
+                        self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+                    self.out_buf = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    # the extra sets are a convenience of the host side: fall back to what the device needs
+                    self.gt_buf = self.anc_buf = self.out_buf = None
+                    if nbuf <= 2:
+                        raise
+                    nbuf = 2
+                    torch.cuda.empty_cache()
+            self.nbuf = nbuf
             self.queues_everything = nbuf >= len(bounds)
-            self.gt_buf = [torch.empty(gt_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
-            self.anc_buf = [None] * nbuf
-            if plan.has_ancestry:
-                self.anc_buf = [torch.empty(anc_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             if result == "bits":
                 tiles = (chunk + TILE - 1) // TILE
                 self.bits = torch.empty((tiles, H, 32, 2), dtype=torch.int32, device=dev)
-            self.out_buf = [torch.empty(out_bytes, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
             self.out_pageable = _pageable(self.out_ptr, out.nbytes)
             self.src_pageable = _pageable(r0.ptr, r0.width * r0.rows)  # its uploads are host copy engine jobs the loop waits for
             self.planes = alloc_planes(chunk, plan.n_keys, dev)
