@@ -425,7 +425,8 @@ int launch_pack_sm2_anc_tma(const PackArgs& a, cudaStream_t st) {
     if (grid == 0) return HT_OK;
     // 32-bit item arithmetic unless the launch has 2^32 items or more (the index of the first item past the end,
     // computed by every CTA, must fit too)
-    const bool wide = w.total + ((int64_t)4 * (grid + 1) << w.chunk_log2) >= ((int64_t)1 << 32);
+    const char* wide_env = getenv("HT_TMA_WIDE");  // tests: the 64-bit instance on small inputs
+    const bool wide = w.total + ((int64_t)4 * (grid + 1) << w.chunk_log2) >= ((int64_t)1 << 32) || (wide_env && atoi(wide_env));
     auto kernel = wide ? pack_sm2_anc_tma_kernel<uint64_t> : pack_sm2_anc_tma_kernel<uint32_t>;
     HT_CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
     kernel<<<grid, kTmaThreads, kTmaSmem, st>>>(map_gt, map_anc, a, w);

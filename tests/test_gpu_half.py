@@ -126,10 +126,50 @@ def test_ancestry_pack_forms_vs_oracle(monkeypatch, form, n, p, H):
     cols = ref_col.astype(np.int64)
     want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs, anc[:, cols], hap_label.astype(np.uint8))
     dplan = engine.DevicePlan(plan)
-    out = engine.transform_device(torch.from_numpy(gt).cuda(), dplan, ancestry=torch.from_numpy(anc).cuda(),
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = engine.transform_device(torch.from_numpy(gt).cuda(), dplan, ancestry=torch.from_numpy(anc).cuda(), flags=flags,
                                   pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC if p % 8 == 0 else _cuda.HT_PACK_AUTO)
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want, err_msg=form)
+    # the QC side channel: missing / multi-allelic calls in REFERENCED columns only
+    sub = gt[:, plan.var_col.astype(np.int64)]
+    want_flags = (1 if (sub >= 254).any() else 0) | (2 if ((sub >= 2) & (sub < 254)).any() else 0)
+    assert int(flags.item()) == want_flags, form
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("group,chunk", [("0", "1"), ("1", "2"), ("3", "4"), ("64", "1")])
+def test_ancestry_tma_pack_item_orders(monkeypatch, wide, group, chunk):
+    """Item orders of the TMA-fed ancestry pack (HT_TMA_GROUP column blocks per group, HT_TMA_CHUNK consecutive
+    items per CTA) and its 64-bit item arithmetic (HT_TMA_WIDE=1: the instance for launches of 2^32 items or
+    more), multi-allelic calls in the data, several tiles and a ragged last column block: against the oracle."""
+    from haptools_b200 import _cuda
+
+    monkeypatch.setenv("HT_PACK_ANC_KERNEL", "tma")
+    monkeypatch.setenv("HT_TMA_WIDE", wide)
+    monkeypatch.setenv("HT_TMA_GROUP", group)
+    monkeypatch.setenv("HT_TMA_CHUNK", chunk)
+    rng = np.random.default_rng(5)
+    n, p, H = 2300, 328, 500
+    gt = rng.integers(0, 2, size=(n, p, 2), dtype=np.uint8)
+    gt[rng.random((n, p, 2)) < 0.01] = 255
+    gt[rng.random((n, p, 2)) < 0.002] = 3
+    anc = np.ascontiguousarray(np.repeat(rng.integers(0, 5, size=(n, (p + 6) // 7, 2), dtype=np.uint8), 7, axis=1)[:, :p])
+    k = rng.integers(0, 7, size=H)
+    hap_off = np.concatenate([[0], np.cumsum(k)])
+    ref_col = np.concatenate([np.sort(rng.choice(p, size=int(x), replace=False)) for x in k] + [np.zeros(0, dtype=np.int64)])
+    ref_allele = rng.integers(0, 2, size=len(ref_col))
+    hap_label = rng.integers(0, 5, size=H)
+    plan = plan_from_refs(ref_col, ref_allele, hap_off, p, np.repeat(hap_label, k))
+    idxs = [np.arange(hap_off[h], hap_off[h + 1]) for h in range(H)]
+    cols = ref_col.astype(np.int64)
+    want = orc.transform_core(gt[:, cols], ref_allele.astype(np.uint8), idxs, anc[:, cols], hap_label.astype(np.uint8))
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = engine.transform_device(torch.from_numpy(gt).cuda(), engine.DevicePlan(plan), ancestry=torch.from_numpy(anc).cuda(),
+                                  flags=flags, pack_mode=_cuda.HT_PACK_SAMPLE_MAJOR_BIALLELIC)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.bool_), want)
+    assert int(flags.item()) == 3
 
 
 @pytest.mark.parametrize("layout", ["C", "C3", "F"])
