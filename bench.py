@@ -560,7 +560,8 @@ def stream_workload(c, args):
         "full_config_estimate_s": best["packed_s"] / best["chunks"] * full_chunks,
         "verified_against_oracle": verified,
         "workload": w["name"] + f"; bounded sample: its first {args.stream_chunks} chunks ({V} variants) and the {Hs} haplotypes inside them",
-        "launches": best["chunks"] + 1,
+        # per chunk: narrow_i32_rows_kernel + pack_vm_kernel (one pack_generic_kernel with HT_I32_KERNEL=generic); + 1 transform
+        "launches": best["chunks"] * (1 if os.environ.get("HT_I32_KERNEL", "")[:1] == "g" else 2) + 1,
     }
 
 

@@ -1301,6 +1301,67 @@ static int launch_tiled(K kernel, const PackArgs& a, int64_t n_xblocks, int64_t 
     return HT_OK;
 }
 
+// variant-major kernel over all (tile, variant) items
+static int launch_pack_vm(const PackArgs& a, bool anc, cudaStream_t st) {
+    const int64_t n_tiles = ht_num_tiles(a.n);
+    const int64_t want = (n_tiles * a.n_vars + kPackWarps - 1) / kPackWarps;
+    if (want <= 0) return HT_OK;
+    // Grid: whole waves of resident CTAs (4 per SM), about 48 items per warp -- 2 waves on the
+    // 1000G-scale config (103.6 us against 107.1 at 8 and 126.9 at 32), 32 waves at 200 k samples x
+    // 50 k variants (3.69 ms against 3.75 at 8); profiles/exp_pack_vm.py.  HT_VM_WAVES / HT_VM_ORDER
+    // override the choice (measurements, tests).
+    const char* waves_env = getenv("HT_VM_WAVES");
+    const int env_waves = waves_env ? atoi(waves_env) : 0;
+    const int64_t n_items = n_tiles * a.n_vars, wave_warps = (int64_t)148 * 4 * kPackWarps;
+    const int64_t waves = env_waves > 0 ? env_waves : max((int64_t)2, min((int64_t)32, (n_items + 24 * wave_warps) / (48 * wave_warps)));
+    const unsigned grid = (unsigned)min(want, (int64_t)148 * 4 * waves);
+    // Item order: variant-first (neighbouring warps read neighbouring pieces of one variant row) is
+    // faster at every size measured: 107.1 against 114.8 us (1000G-scale), 3.75 against 3.83 ms (200 k)
+    const char* order = getenv("HT_VM_ORDER");  // "t": tile-first
+    const bool vfirst = order ? order[0] != 't' : true;
+    if (anc) pack_vm_kernel<true><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
+    else pack_vm_kernel<false><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
+    HT_CUDA_TRY(cudaGetLastError());
+    return HT_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// pgenlib int32 allele codes -> bytes, referenced rows only: row i of `dst` = the 2n codes of variant
+// var_col[i] as the reference stores them in its uint8 matrix (haptools/data/genotypes.py:1388-1401: -9 -> 255,
+// everything else modulo 256), i.e. a variant-major byte matrix the variant-major pack kernel reads.  Pure
+// streaming: a lane turns one 16-byte load (2 samples x 2 strands) into one 4-byte store.
+// -----------------------------------------------------------------------------------------
+constexpr int kNarrowPerThread = 4;  // 16-byte loads per thread
+
+__device__ __forceinline__ uint32_t narrow4(int4 v) {
+    const uint32_t b0 = v.x == -9 ? 255u : (uint32_t)v.x, b1 = v.y == -9 ? 255u : (uint32_t)v.y;
+    const uint32_t b2 = v.z == -9 ? 255u : (uint32_t)v.z, b3 = v.w == -9 ? 255u : (uint32_t)v.w;
+    return prmt(prmt(b0, b1, 0x0040), prmt(b2, b3, 0x0040), 0x5410);  // low bytes of the four
+}
+
+__global__ void __launch_bounds__(256)
+narrow_i32_rows_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const uint32_t* __restrict__ var_col,
+                       int64_t n_values, uint32_t blocks_per_row, uint8_t* __restrict__ dst, int64_t dst_pitch,
+                       uint32_t* __restrict__ ident) {
+    const uint32_t row = blockIdx.x / blocks_per_row, xb = blockIdx.x % blocks_per_row;
+    if (xb == 0 && threadIdx.x == 0) ident[row] = row;
+    const int4* s = reinterpret_cast<const int4*>(src + (int64_t)__ldg(var_col + row) * src_pitch);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + (int64_t)row * dst_pitch);
+    const int64_t n4 = n_values >> 2;
+    const int64_t i0 = (int64_t)xb * (256 * kNarrowPerThread) + threadIdx.x;
+    int4 v[kNarrowPerThread];
+#pragma unroll
+    for (int u = 0; u < kNarrowPerThread; ++u)
+        if (i0 + 256 * u < n4) v[u] = __ldg(s + i0 + 256 * u);
+#pragma unroll
+    for (int u = 0; u < kNarrowPerThread; ++u)
+        if (i0 + 256 * u < n4) d[i0 + 256 * u] = narrow4(v[u]);
+    if (xb == blocks_per_row - 1 && threadIdx.x < (n_values & 3)) {  // 2n values: a tail of 2 when n is odd
+        const int32_t x = reinterpret_cast<const int32_t*>(s)[4 * n4 + threadIdx.x];
+        reinterpret_cast<uint8_t*>(d)[4 * n4 + threadIdx.x] = x == -9 ? (uint8_t)255 : (uint8_t)x;
+    }
+}
+
 static int check_pack(const PackArgs& a) {
     if (a.n < 0 || a.n_vars < 0 || a.n_keys < 0 || a.key_base < 0) return bad_arg("negative size");
     if (a.n_vars == 0 || a.n == 0) return HT_OK;
@@ -1363,27 +1424,7 @@ int ht_pack_u8(const uint8_t* gt, int64_t gt_s_samp, int64_t gt_s_var, int64_t g
                 set_error("variant-major pack needs s_strand=1, s_samp=2 and 16-byte aligned rows");
                 return HT_ERR_UNSUPPORTED;
             }
-            {
-                const int64_t n_tiles = ht_num_tiles(a.n);
-                const int64_t want = (n_tiles * a.n_vars + kPackWarps - 1) / kPackWarps;
-                // Grid: whole waves of resident CTAs (4 per SM), about 48 items per warp -- 2 waves on the
-                // 1000G-scale config (103.6 us against 107.1 at 8 and 126.9 at 32), 32 waves at 200 k samples x
-                // 50 k variants (3.69 ms against 3.75 at 8); profiles/exp_pack_vm.py.  HT_VM_WAVES / HT_VM_ORDER
-                // override the choice (measurements, tests).
-                const char* waves_env = getenv("HT_VM_WAVES");
-                const int env_waves = waves_env ? atoi(waves_env) : 0;
-                const int64_t n_items = n_tiles * a.n_vars, wave_warps = (int64_t)148 * 4 * kPackWarps;
-                const int64_t waves = env_waves > 0 ? env_waves : max((int64_t)2, min((int64_t)32, (n_items + 24 * wave_warps) / (48 * wave_warps)));
-                const unsigned grid = (unsigned)min(want, (int64_t)148 * 4 * waves);
-                // Item order: variant-first (neighbouring warps read neighbouring pieces of one variant row) is
-                // faster at every size measured: 107.1 against 114.8 us (1000G-scale), 3.75 against 3.83 ms (200 k)
-                const char* order = getenv("HT_VM_ORDER");  // "t": tile-first
-                const bool vfirst = order ? order[0] != 't' : true;
-                if (anc) pack_vm_kernel<true><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
-                else pack_vm_kernel<false><<<grid, kPackThreads, 0, st>>>(a, n_tiles, vfirst);
-                HT_CUDA_TRY(cudaGetLastError());
-                return HT_OK;
-            }
+            return launch_pack_vm(a, anc != nullptr, st);
         case HT_PACK_SAMPLE_MAJOR: {
             if (!sm_ok) {
                 set_error("sample-major pack needs s_strand=1, s_var=2, 4-byte aligned rows and col_var");
@@ -1477,6 +1518,36 @@ int ht_pack_i32_anc(const int32_t* alleles, int64_t row_pitch_elems, int64_t n_s
     if (n_vars == 0 || n_samples == 0) return HT_OK;
     if (row_pitch_elems < 2 * n_samples) return bad_arg("row_pitch_elems < 2 * n_samples");
     if (!aligned(alleles, a.gv, 8)) return bad_arg("int32 allele rows must be 8-byte aligned");
+    // Without ancestry labels: narrow the referenced rows to bytes (what the reference's uint8 matrix holds) and run
+    // the variant-major pack kernel on them -- 2 streaming kernels, 4 x the rate of the generic ballot kernel on the
+    // streamed-PGEN config.  HT_I32_KERNEL=generic keeps the one-kernel form (measurements, tests).
+    const char* form = getenv("HT_I32_KERNEL");
+    if (!anc && !(form && form[0] == 'g') && aligned(alleles, a.gv, 16) && n_vars < ((int64_t)1 << 31)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int64_t n_values = 2 * n_samples, dst_pitch = (n_values + 15) / 16 * 16;
+        const int64_t blocks_per_row = (n_values / 4 + 256 * kNarrowPerThread - 1) / (256 * kNarrowPerThread);
+        if (blocks_per_row > 0 && blocks_per_row * n_vars < ((int64_t)1 << 31)) {
+            uint8_t* scratch = nullptr;
+            const size_t bytes = (size_t)n_vars * (size_t)dst_pitch;
+            HT_CUDA_TRY(cudaMallocAsync((void**)&scratch, bytes + sizeof(uint32_t) * (size_t)n_vars, st));
+            uint32_t* ident = reinterpret_cast<uint32_t*>(scratch + bytes);  // bytes is a multiple of 16
+            narrow_i32_rows_kernel<<<(unsigned)(blocks_per_row * n_vars), 256, 0, st>>>(
+                a.gt, a.gv, var_col, n_values, (uint32_t)blocks_per_row, scratch, dst_pitch, ident);
+            cudaError_t e = cudaGetLastError();
+            int rc = HT_OK;
+            if (e == cudaSuccess) {
+                PackArgs b = a;
+                b.gt = scratch; b.gs = 2; b.gv = dst_pitch; b.gc = 1;
+                b.var_col = ident;
+                rc = launch_pack_vm(b, false, st);
+            }
+            const cudaError_t ef = cudaFreeAsync(scratch, st);
+            if (e != cudaSuccess) return cuda_fail(e, "narrow_i32_rows_kernel");
+            if (rc) return rc;
+            HT_CUDA_TRY(ef);
+            return HT_OK;
+        }
+    }
     const int64_t n_vblocks = (n_vars + kPackWarps - 1) / kPackWarps;
     return anc ? launch_tiled(pack_generic_kernel<LoadI32, true>, a, n_vblocks, 0, false, (cudaStream_t)stream)
                : launch_tiled(pack_generic_kernel<LoadI32, false>, a, n_vblocks, 0, false, (cudaStream_t)stream);

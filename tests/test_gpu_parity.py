@@ -362,9 +362,15 @@ def test_fused_allele_counts_and_maf():
 
 
 # ------------------------------------------------------------------ pgenlib int32 buffers
-def test_pack_i32_chunks():
-    rng = np.random.default_rng(11)
-    n, p, H = 1500, 96, 50
+@pytest.mark.parametrize("form", ["narrow", "generic"])
+@pytest.mark.parametrize("n", [1500, 1501, 2048, 37])
+def test_pack_i32_chunks(monkeypatch, form, n):
+    """ht_pack_i32 in both forms (csrc/ht_pack.cu): int32 rows narrowed to bytes + the variant-major kernel (the
+    default), and the one-kernel generic form; odd sample counts exercise the narrowing kernel's 2-value tail and
+    the 16-byte alignment rule of its rows, flags are compared with the definition."""
+    monkeypatch.setenv("HT_I32_KERNEL", form)
+    rng = np.random.default_rng(11 + n)
+    p, H = 96, 50
     gt, _, plan, want = _random_arrays(rng, n, p, H, multi=True, missing=0.05)
     # what PgenReader.read_alleles_list hands out: (variants, 2n) int32, -9 = missing
     alleles = gt.transpose(1, 0, 2).reshape(p, 2 * n).astype(np.int32)
@@ -375,6 +381,7 @@ def test_pack_i32_chunks():
     lib = _cuda.lib()
     chunk = 40
     vk = plan.var_key_off.astype(np.int64)
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
     for c0 in range(0, p, chunk):
         c1 = min(p, c0 + chunk)
         sel = np.nonzero((plan.var_col >= c0) & (plan.var_col < c1))[0]
@@ -387,7 +394,7 @@ def test_pack_i32_chunks():
         kall = torch.from_numpy(plan.key_allele[vk[v0] : vk[v1]].copy()).cuda()
         _cuda.check(
             lib.ht_pack_i32(buf.data_ptr(), 2 * n, n, rows.data_ptr(), koff.data_ptr(), kall.data_ptr(),
-                            v1 - v0, int(vk[v0]), plan.n_keys, planes.data_ptr(), 0, 0),
+                            v1 - v0, int(vk[v0]), plan.n_keys, planes.data_ptr(), flags.data_ptr(), 0),
             "ht_pack_i32",
         )
     torch.cuda.synchronize()
@@ -395,6 +402,9 @@ def test_pack_i32_chunks():
     engine.transform_u8(dplan, planes, n, out.data_ptr(), out.stride(0))
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out[:, : 2 * H].cpu().numpy().reshape(n, H, 2).view(np.bool_), want)
+    sub = gt[:, plan.var_col.astype(np.int64)]
+    want_flags = (1 if (sub >= 254).any() else 0) | (2 if ((sub >= 2) & (sub < 254)).any() else 0)
+    assert int(flags.item()) == want_flags
 
 
 @pytest.mark.parametrize("chunk", [7, 64, 1000])
