@@ -850,6 +850,47 @@ def run_b200(args):
                          "nvlink5_per_direction_GBps": 900, "own_shard_intact": all_ranks(same),
                          "what": "dist.allgather_bits: NCCL all_gather_into_tensor of the bit-packed result (tiles, H, 32, 2), "
                                  "tile-major so the gather is a concatenation; CUDA events, max over ranks"}
+            # ---- the same pair as ONE kernel: ht_transform_bits_gather stores every record of this rank's shard into
+            # all ranks' gathered buffers over NVLink peer memory (dist.PeerGather); timed from the planes to the
+            # complete gathered result on every rank, against transform_bits + NCCL all-gather for the same
+            fused = None
+            try:
+                e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for _ in range(2):
+                    engine.transform_bits(dplan, planes, n, bits)
+                    gathered = hdist.allgather_bits(bits, n_gather)
+                barrier()
+                e2.record()
+                for _ in range(reps):
+                    engine.transform_bits(dplan, planes, n, bits)
+                    gathered = hdist.allgather_bits(bits, n_gather)
+                e3.record()
+                barrier()
+                pair_ms = max_over_ranks(e2.elapsed_time(e3)) / reps
+                pg = hdist.PeerGather(n_gather, H)
+                for _ in range(2):
+                    fbits = pg.run(dplan, planes, n)
+                barrier()
+                e2.record()
+                for _ in range(reps):
+                    fbits = pg.run(dplan, planes, n)
+                e3.record()
+                barrier()
+                fused_ms = max_over_ranks(e2.elapsed_time(e3)) / reps
+                total_tiles = (n_gather + engine.TILE - 1) // engine.TILE
+                same_f = bool(torch.equal(fbits[:total_tiles], gathered[:total_tiles]))
+                barrier()
+                fused = {"ms": fused_ms, "transform_bits_plus_nccl_allgather_ms": pair_ms, "speedup": pair_ms / fused_ms,
+                         "busbw_GBps": shard_bytes * (world - 1) / (fused_ms * 1e-3) / 1e9,
+                         "equals_nccl_result": all_ranks(same_f),
+                         "what": "dist.PeerGather: ht_transform_bits_gather (AND + record stores into every rank's buffer over "
+                                 "NVLink peer memory, CUDA IPC) + a stream-ordered one-element all-reduce as the closing barrier; "
+                                 "CUDA events from the planes to the complete gathered result, max over ranks"}
+                del fbits
+                pg.close()
+            except Exception as e:  # noqa: BLE001 -- peer memory may be unavailable on a box (no P2P / IPC)
+                fused = {"skipped": f"{type(e).__name__}: {e}"[:300]}
+            allgather["fused_kernel"] = fused
             del gathered, bits
         except torch.cuda.OutOfMemoryError:
             allgather = {"skipped": "not enough HBM next to the resident shard"}

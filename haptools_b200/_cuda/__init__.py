@@ -12,7 +12,7 @@ import os
 
 # HT_LIB_PATH lets experiments (profiles/) load an alternative build of the same ABI
 LIB_PATH = Path(os.environ.get("HT_LIB_PATH") or Path(__file__).resolve().parent / "libhaptools_cuda.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 HT_OK, HT_ERR_BAD_ARG, HT_ERR_CUDA, HT_ERR_UNSUPPORTED = 0, 1, 2, 3
 HT_FLAG_MISSING, HT_FLAG_NON_BIALLELIC = 1, 2
@@ -58,6 +58,11 @@ SIGNATURES = {
     "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "ht_transform_u8_staged": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "ht_transform_bits_gather": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i32, _i64, _p]),
+    "ht_peer_alloc": (_i32, [_sz, _p, _p]),
+    "ht_peer_open": (_i32, [_p, _p]),
+    "ht_peer_close": (_i32, [_p]),
+    "ht_peer_free": (_i32, [_p]),
     "ht_transform_bits_local": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "ht_unpack_bits_u8": (_i32, [_p, _i64, _i64, _p, _i64, _p]),
     "ht_local_workspace_bytes": (_sz, [_i64, _i64]),

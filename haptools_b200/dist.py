@@ -2,8 +2,9 @@
 Multi-GPU execution of the transform: one process per GPU, samples sharded, NO communication
 on the hot path (out[s, :, :] depends only on sample s).  The index tables
 (a few MB) are replicated on every rank.  The only collective is an optional all-gather of
-the bit-packed result (1/8 of the uint8 bytes) over torch.distributed (NCCL on GPUs; the
-host-side logic is covered with gloo on CPU).
+the bit-packed result (1/8 of the uint8 bytes): `allgather_bits` over torch.distributed (NCCL on GPUs; the
+host-side logic is covered with gloo on CPU), or `PeerGather`, where the transform kernel itself stores every
+record into all ranks' gathered buffers over NVLink peer memory (compute and transfer in one kernel).
 """
 from __future__ import annotations
 
@@ -48,6 +49,95 @@ def allgather_bits(local_bits: torch.Tensor, n_samples: int, group=None) -> torc
     dist.all_gather_into_tensor(out, send.contiguous(), group=group)
     tiles = (n_samples + TILE - 1) // TILE
     return out[:tiles]
+
+
+class _DevMem:
+    """A raw device address as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+class PeerGather:
+    """
+    The gathered bit-packed result (tiles_total, H, 32, 2) of a sample-sharded cohort on EVERY rank, filled by
+    `ht_transform_bits_gather`: each rank's transform kernel stores the records of its own shard into its own buffer
+    and, through NVLink / NVSwitch peer memory, into every other rank's -- the all-gather is the kernel's stores,
+    overlapped with the AND arithmetic record by record, instead of a collective that starts when the kernel ends.
+
+    One process per GPU of one node (torch.distributed initialised, backend NCCL).  Buffers are allocated by the
+    library (cudaMalloc: CUDA IPC handles need that), exchanged as 64-byte handles through the process group and
+    mapped with lazy peer access.  `run()` is asynchronous on the current stream; the buffer is complete on every
+    rank once the stream has passed the one-element all-reduce `run()` ends with (stream-ordered on every rank: it
+    completes only when all ranks have reached it, i.e. when all their kernels -- and their remote stores -- are
+    done).  world_size 1 works without a process group.
+    """
+
+    def __init__(self, n_samples: int, n_haps: int, device=None, group=None):
+        import ctypes
+
+        from . import _cuda
+
+        self.lib, self._check = _cuda.lib(), _cuda.check
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 16:
+            raise ValueError("PeerGather serves the GPUs of one node (at most 16 ranks)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_samples, self.n_haps = int(n_samples), int(n_haps)
+        self.per = shard_tiles(n_samples, self.world)  # tiles per rank (equal shards)
+        self.tiles = self.per * self.world
+        nbytes = max(self.tiles * self.n_haps * 256, 256)
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ht_peer_alloc(nbytes, ctypes.byref(own), handle), "ht_peer_alloc")
+            self._own = own.value
+            handles = [handle.raw]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle.raw, group=group)
+            self.ptrs, self._opened = [], []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs.append(self._own)
+                    continue
+                peer = ctypes.c_void_p()
+                self._check(self.lib.ht_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(peer)), "ht_peer_open")
+                self.ptrs.append(peer.value)
+                self._opened.append(peer.value)
+        self._dsts = (ctypes.c_void_p * self.world)(*self.ptrs)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        total_tiles = (self.n_samples + TILE - 1) // TILE
+        self.bits = torch.as_tensor(_DevMem(self._own, (self.tiles, self.n_haps, 32, 2)), device=self.device)[:total_tiles]
+
+    def run(self, dplan, planes: torch.Tensor, n_local: int, stream=None) -> torch.Tensor:
+        """This rank's shard (n_local samples, `shard_bounds`) -> its records in every rank's buffer; returns the
+        gathered tensor of THIS rank (complete when the stream has passed the closing all-reduce)."""
+        if n_local > self.per * TILE:
+            raise ValueError("shard larger than shard_tiles(n_samples, world) tiles")
+        st = stream or torch.cuda.current_stream(self.device)
+        self._check(self.lib.ht_transform_bits_gather(
+            planes.data_ptr() if planes is not None and planes.numel() else None, n_local, dplan.plan.n_keys,
+            dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr() if dplan.hap_key.numel() else None, self.n_haps,
+            self._dsts, self.world, self.rank * self.per, st.cuda_stream), "ht_transform_bits_gather")
+        if self.world > 1:
+            with torch.cuda.stream(st):
+                dist.all_reduce(self._flag, group=self.group)
+        return self.bits
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free one's own (all ranks, after a barrier of the caller's)."""
+        if getattr(self, "_own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self.lib.ht_peer_close(p)
+            self._opened = []
+            self.bits = None
+            self.lib.ht_peer_free(self._own)
+            self._own = None
 
 
 def pack_result_bits(out_bool: np.ndarray) -> np.ndarray:

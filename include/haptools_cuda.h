@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define HT_ABI_VERSION 8
+#define HT_ABI_VERSION 9
 
 #define HT_TILE_SAMPLES 1024 /* samples per plane tile            */
 #define HT_TILE_WORDS 32     /* 32-bit words per tile per strand  */
@@ -240,6 +240,34 @@ int ht_transform_u8_staged(const uint32_t* planes, int64_t n_samples, int64_t n_
 int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
                       const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
                       uint32_t* out_bits, void* stream);
+
+/*
+ * K2 bit-packed + all-gather in ONE kernel (the optional collective of the path, north_star: "NCCL is used only
+ * for an optional allgather of the packed result" -- this is the NVLink-native form of that pair): every rank
+ * computes the records of its own sample shard and stores each of them into the gathered result of EVERY rank,
+ * dsts[0 .. n_dsts) = device addresses of the ranks' (tiles_total, n_haps, 32, 2) buffers (its own and its peers',
+ * mapped through ht_peer_open), at tile dst_tile0 + local tile.  The transfer is the kernel's own stores over
+ * NVLink / NVSwitch peer memory and overlaps the AND arithmetic record by record; what is left for the caller is a
+ * barrier across ranks once the kernel has finished on all of them (haptools_b200.dist.PeerGather does it with a
+ * stream-ordered one-element all-reduce).  n_dsts <= HT_MAX_PEERS.  With n_dsts == 1 and dst_tile0 == 0 it is
+ * ht_transform_bits.
+ */
+#define HT_MAX_PEERS 16
+int ht_transform_bits_gather(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
+                             const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
+                             uint32_t* const* dsts, int32_t n_dsts, int64_t dst_tile0, void* stream);
+
+/*
+ * Peer memory for ht_transform_bits_gather, one process per GPU: ht_peer_alloc gives device memory of the current
+ * device (cudaMalloc, zero-filled) and the 64-byte handle another process of the node turns into an address of its
+ * own with ht_peer_open (cudaIpcGetMemHandle / cudaIpcOpenMemHandle with lazy peer access).  ht_peer_close unmaps a
+ * peer's buffer, ht_peer_free releases one's own.
+ */
+#define HT_PEER_HANDLE_BYTES 64
+int ht_peer_alloc(size_t bytes, void** ptr, void* handle);
+int ht_peer_open(const void* handle, void** ptr);
+int ht_peer_close(void* ptr);
+int ht_peer_free(void* ptr);
 
 /*
  * K2, two-phase ("local") form: same results as ht_transform_u8 / ht_transform_bits with fewer
