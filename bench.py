@@ -888,7 +888,8 @@ def run_b200(args):
                                  "CUDA events from the planes to the complete gathered result, max over ranks"}
                 del fbits
                 pg.close()
-            except Exception as e:  # noqa: BLE001 -- peer memory may be unavailable on a box (no P2P / IPC)
+            except Exception as e:  # noqa: BLE001 -- peer memory may be unavailable on a box (no P2P / IPC);
+                # PeerGather raises on ALL ranks together, so nobody is left waiting in a collective
                 fused = {"skipped": f"{type(e).__name__}: {e}"[:300]}
             allgather["fused_kernel"] = fused
             del gathered, bits

@@ -90,22 +90,47 @@ class PeerGather:
         self.tiles = self.per * self.world
         nbytes = max(self.tiles * self.n_haps * 256, 256)
         own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        self._own, self.ptrs, self._opened = None, [], []
         with torch.cuda.device(self.device):
-            self._check(self.lib.ht_peer_alloc(nbytes, ctypes.byref(own), handle), "ht_peer_alloc")
-            self._own = own.value
-            handles = [handle.raw]
+            # Every step that can fail on ONE rank is followed by an exchange, so that all ranks raise together
+            # (a rank that left alone would leave the others waiting in the next collective).
+            err = None
+            rc = self.lib.ht_peer_alloc(nbytes, ctypes.byref(own), handle)
+            if rc == 0:
+                self._own = own.value
+            else:
+                err = f"ht_peer_alloc: {self.lib.ht_last_error().decode('utf-8', 'replace')}"
+            handles = [handle.raw if err is None else None]
             if self.world > 1:
                 handles = [None] * self.world
-                dist.all_gather_object(handles, handle.raw, group=group)
-            self.ptrs, self._opened = [], []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.ptrs.append(self._own)
-                    continue
-                peer = ctypes.c_void_p()
-                self._check(self.lib.ht_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(peer)), "ht_peer_open")
-                self.ptrs.append(peer.value)
-                self._opened.append(peer.value)
+                dist.all_gather_object(handles, handle.raw if err is None else None, group=group)
+            if err is None and any(h is None for h in handles):
+                err = "another rank could not allocate its buffer"
+            if err is None:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.ptrs.append(self._own)
+                        continue
+                    peer = ctypes.c_void_p()
+                    rc = self.lib.ht_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(peer))
+                    if rc != 0:
+                        err = f"ht_peer_open(rank {r}): {self.lib.ht_last_error().decode('utf-8', 'replace')}"
+                        break
+                    self.ptrs.append(peer.value)
+                    self._opened.append(peer.value)
+            if self.world > 1:
+                errs = [None] * self.world
+                dist.all_gather_object(errs, err, group=group)
+                err = next((f"rank {r}: {e}" for r, e in enumerate(errs) if e is not None), None)
+            if err is not None:
+                for pp in self._opened:
+                    self.lib.ht_peer_close(pp)
+                if self._own is not None:
+                    self.lib.ht_peer_free(self._own)
+                self._own, self._opened = None, []
+                from ._cuda import HaptoolsCudaError
+
+                raise HaptoolsCudaError(f"PeerGather: {err}")
         self._dsts = (ctypes.c_void_p * self.world)(*self.ptrs)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         total_tiles = (self.n_samples + TILE - 1) // TILE
