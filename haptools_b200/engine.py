@@ -541,13 +541,14 @@ class _HostPipe:
             # them take the host waits out of the loop that queues the chunks: with a buffer set per chunk nothing
             # is reused, so the one Python thread queues the whole call in a few ms and then sits in finish() with
             # the GIL released -- whatever else runs in the interpreter (the class API's helper thread) no longer
-            # delays a chunk.  Bounded by a quarter of the free device memory (HAPTOOLS_B200_PIPE_DEPTH overrides).
+            # delays a chunk.  Bounded by a quarter of the free device memory and 16 GB (HAPTOOLS_B200_PIPE_DEPTH
+            # overrides): enough for 128 k samples of the UKB-scale plan per call.
             depth = os.environ.get("HAPTOOLS_B200_PIPE_DEPTH", "").strip()
             if depth:
                 want = max(2, int(depth))
             else:
                 free = torch.cuda.mem_get_info(dev)[0]
-                want = max(2, int(free // 4 // max(gt_bytes + anc_bytes + out_bytes, 1)))
+                want = max(2, int(min(free // 4, 16 << 30) // max(gt_bytes + anc_bytes + out_bytes, 1)))
             nbuf = min(want, len(bounds))
             while True:
                 try:
