@@ -807,7 +807,16 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
     if len(devs) > 1 and not chunk_samples:  # at least two chunks per device keep its three streams busy
         chunk = min(chunk, max(TILE, -(-n // (2 * len(devs))) // TILE * TILE))
     chunk = min(n, max(TILE, chunk // TILE * TILE)) if chunk < n else n
-    bounds = _ramped_bounds(n, chunk, len(devs)) if not chunk_samples else [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+    # Row-gather uploads (variant-major array, few referenced variants) of a small call go in TWO even chunks instead
+    # of the ramp: cutting the samples cuts every gathered row into pieces (5 KB rows of the 1000G-scale call ->
+    # 0.5-2 KB in a ramp of five), and with 0.13 ms of kernels there is little to overlap (13.3-13.9 ms against
+    # 14.8-15.2 ms; one chunk: 13.9-14.2 ms; profiles/r2/e2e_1000g_chunks.json)
+    even = (not chunk_samples and len(devs) == 1 and n > 512 and _gatherable(gt, plan)
+            and (ancestry is None or _gatherable(ancestry, plan))
+            and upload_bytes(gt, plan, ancestry) <= (1 << 30) and out.nbytes <= (256 << 20))
+    if even:
+        chunk = -(-(-(-n // 2)) // 256) * 256  # half of the samples, rounded up to 256
+    bounds = _ramped_bounds(n, chunk, len(devs)) if not (chunk_samples or even) else [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
     devs = devs[: len(bounds)]
     if result == "auto":
         result = os.environ.get("HAPTOOLS_B200_RESULT", "").strip().lower() or "auto"
