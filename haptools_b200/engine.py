@@ -431,6 +431,11 @@ def _ramped_bounds(n: int, chunk: int, n_devs: int = 1):
     return bounds
 
 
+def _half_chunk(n: int) -> int:
+    """Chunk size that cuts n samples into two pieces: half of them, rounded up to a multiple of 256."""
+    return -(-(-(-n // 2)) // 256) * 256
+
+
 # Result arrays of transform_host(out=None): like the reference's np.empty (haplotypes.py:1408), except that the
 # memory of a result the caller has DROPPED is handed out again.  A fresh multi-GB np.empty is first touched
 # page by page while it is filled (the kernel zeroes every page: 30 ms of the 72 ms a 3.3 GB result takes), and
@@ -815,7 +820,7 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
             and (ancestry is None or _gatherable(ancestry, plan))
             and upload_bytes(gt, plan, ancestry) <= (1 << 30) and out.nbytes <= (256 << 20))
     if even:
-        chunk = -(-(-(-n // 2)) // 256) * 256  # half of the samples, rounded up to 256
+        chunk = _half_chunk(n)
     bounds = _ramped_bounds(n, chunk, len(devs)) if not (chunk_samples or even) else [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
     devs = devs[: len(bounds)]
     if result == "auto":

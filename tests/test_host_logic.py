@@ -21,6 +21,14 @@ def test_ramped_bounds_cover_every_sample_once(n, chunk, devs):
         assert max(sizes) == chunk or len(bounds) <= 3 * devs + 2  # (many devices: the ramp alone may cover n)
 
 
+@pytest.mark.parametrize("n", [513, 1025, 2048, 2049, 2504, 4096, 5000, 100_001])
+def test_half_chunk_makes_two_pieces(n):
+    chunk = engine._half_chunk(n)
+    bounds = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+    assert chunk % 256 == 0 and len(bounds) == 2 and bounds[0] == (0, chunk) and bounds[1][1] == n
+    assert bounds[0][1] - bounds[0][0] >= bounds[1][1] - bounds[1][0] > 0
+
+
 def _plan(p, cols):
     cols = np.asarray(cols, dtype=np.int64)
     return plan_from_refs(cols, np.ones(len(cols), dtype=np.int64), np.array([0, len(cols)]), p, None)
