@@ -29,6 +29,23 @@ __global__ void __launch_bounds__(256, 4) stg_kernel(uint8_t* out, int64_t pitch
     }
 }
 
+// CTA = 512 rows x W bytes (W = 512 or 1024): thread = 16 bytes of a row, W / 16 threads per row
+template <int W>
+__global__ void __launch_bounds__(256, 4) stg_wide_kernel(uint8_t* out, int64_t pitch, uint32_t n_wb) {
+    extern __shared__ __align__(128) uint8_t pad[];
+    constexpr int kPerRow = W / 16, kRowsPerPass = 256 / kPerRow;
+    const int64_t ht = blockIdx.x / n_wb, wb = blockIdx.x % n_wb;
+    const int cb = threadIdx.x % kPerRow, g = threadIdx.x / kPerRow;
+    uint8_t* p0 = out + wb * W + 16 * cb + (ht * 512 + g) * pitch;
+    const uint32_t v = threadIdx.x & 1;
+#pragma unroll 4
+    for (int m = 0; m < 512 / kRowsPerPass; ++m) {
+        uint8_t* p = p0 + (int64_t)m * kRowsPerPass * pitch;
+        if (wb * W + 16 * cb < pitch)
+            asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v), "r"(v), "r"(v), "r"(v) : "memory");
+    }
+}
+
 template <int NBUF>
 __global__ void __launch_bounds__(256, 4) tma3d_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t n_hb) {
     extern __shared__ __align__(128) uint8_t smem[];  // NBUF x 2 boxes x 4 KB (+ padding that sets the occupancy)
@@ -77,6 +94,19 @@ int main() {
         int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stg_kernel, 256, pad_kb * 1024);
         float ms = timeit([&] { stg_kernel<<<n_half * n_hb, 256, pad_kb * 1024>>>(out, pitch, n_hb); });
         printf("stg.cs.v4 from registers, %d CTAs/SM: %7.2f ms  %6.0f GB/s\n", occ, ms, bytes / ms / 1e6);
+    }
+    for (int pad_kb : {29, 53}) {
+        int occ = 0;
+        cudaFuncSetAttribute(stg_wide_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stg_wide_kernel<512>, 256, pad_kb * 1024);
+        uint32_t n_wb = (uint32_t)((pitch + 511) / 512);
+        float ms = timeit([&] { stg_wide_kernel<512><<<n_half * n_wb, 256, pad_kb * 1024>>>(out, pitch, n_wb); });
+        printf("stg.cs.v4, CTA = 512 rows x 512 B, %d CTAs/SM: %7.2f ms  %6.0f GB/s\n", occ, ms, bytes / ms / 1e6);
+        cudaFuncSetAttribute(stg_wide_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stg_wide_kernel<1024>, 256, pad_kb * 1024);
+        n_wb = (uint32_t)((pitch + 1023) / 1024);
+        ms = timeit([&] { stg_wide_kernel<1024><<<n_half * n_wb, 256, pad_kb * 1024>>>(out, pitch, n_wb); });
+        printf("stg.cs.v4, CTA = 512 rows x 1024 B, %d CTAs/SM: %7.2f ms  %6.0f GB/s\n", occ, ms, bytes / ms / 1e6);
     }
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)pitch, 32, (cuuint64_t)(n / 32)};
