@@ -58,7 +58,7 @@ SIGNATURES = {
     "ht_transform_u8": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "ht_transform_u8_staged": (_i32, [_p, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
     "ht_transform_bits": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
-    "ht_transform_bits_gather": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _i32, _i64, _p]),
+    "ht_transform_bits_gather": (_i32, [_p, _i64, _i64, _p, _p, _p, _i64, _p, _i32, _i64, _p]),
     "ht_peer_alloc": (_i32, [_sz, _p, _p]),
     "ht_peer_open": (_i32, [_p, _p]),
     "ht_peer_close": (_i32, [_p]),

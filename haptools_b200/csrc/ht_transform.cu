@@ -421,17 +421,23 @@ struct PeerDsts {
     uint32_t* p[HT_MAX_PEERS];
 };
 
+// kOrdered: warp i of the grid computes haplotype hap_order[i] (the planner's key order: neighbouring warps share
+// plane lines, which the L1 / L2 then serve -- 3 x fewer L2->SM reads than in an arbitrary caller order) and every
+// warp hands its own 256-byte record to the TMA; records scatter at no cost, they are whole and aligned.
+template <bool kOrdered>
 __global__ void __launch_bounds__(kThreads)
 transform_bits_gather_kernel(const uint32_t* __restrict__ planes, int64_t n_samples, int64_t n_keys,
                              const uint32_t* __restrict__ hap_off, const uint32_t* __restrict__ hap_key,
-                             int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0, const PeerDsts dsts, int n_dsts,
-                             int64_t dst_tile0) {
+                             const uint32_t* __restrict__ hap_order, int64_t n_haps, uint32_t n_hap_blocks, int64_t tile0,
+                             const PeerDsts dsts, int n_dsts, int64_t dst_tile0) {
     __shared__ __align__(128) uint2 s_rec[kWarps][kTileWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tile = tile0 + blockIdx.x / n_hap_blocks;
     const int64_t h0 = (int64_t)(blockIdx.x % n_hap_blocks) * kWarps;
-    const int64_t h = h0 + warp;
-    if (h < n_haps) {
+    const int64_t i = h0 + warp;
+    int64_t h = i;
+    if (kOrdered && i < n_haps) h = __ldg(hap_order + i);
+    if (i < n_haps) {
         const uint2* tile_rec =
             reinterpret_cast<const uint2*>(planes) + ((size_t)tile * (size_t)n_keys) * kTileWords + lane;
         uint2 r = and_keys_global(tile_rec, hap_key, __ldg(hap_off + h), __ldg(hap_off + h + 1));
@@ -440,6 +446,23 @@ transform_bits_gather_kernel(const uint32_t* __restrict__ planes, int64_t n_samp
         r.x &= vm;
         r.y &= vm;
         s_rec[warp][lane] = r;
+    }
+    if (kOrdered) {
+        __syncwarp();
+        if (lane == 0 && i < n_haps) {
+            const size_t at = ((size_t)(dst_tile0 + tile) * (size_t)n_haps + (size_t)h) * kTileWords;  // in uint2
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_rec[warp][0]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+            for (int d = 0; d < HT_MAX_PEERS; ++d)
+                if (d < n_dsts)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint2*>(dsts.p[d]) + at),
+                                 "r"(src), "n"(kTileWords * 8)
+                                 : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -589,7 +612,7 @@ int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
 }
 
 int ht_transform_bits_gather(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
-                             const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
+                             const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* hap_order, int64_t n_haps,
                              uint32_t* const* dsts, int32_t n_dsts, int64_t dst_tile0, void* stream) {
     using namespace ht;
     if (int rc = check_common(planes, n_samples, n_keys, hap_off, hap_key, n_haps)) return rc;
@@ -610,8 +633,12 @@ int ht_transform_bits_gather(const uint32_t* planes, int64_t n_samples, int64_t 
     const int64_t tiles_per_launch = max((int64_t)1, (int64_t)0x7fffffff / n_hb);
     for (int64_t t0 = 0; t0 < n_tiles; t0 += tiles_per_launch) {
         const int64_t nt = min(tiles_per_launch, n_tiles - t0);
-        transform_bits_gather_kernel<<<dim3((unsigned)(nt * n_hb)), kThreads, 0, (cudaStream_t)stream>>>(
-            planes, n_samples, n_keys, hap_off, hap_key, n_haps, (uint32_t)n_hb, t0, pd, n_dsts, dst_tile0);
+        if (hap_order)
+            transform_bits_gather_kernel<true><<<dim3((unsigned)(nt * n_hb)), kThreads, 0, (cudaStream_t)stream>>>(
+                planes, n_samples, n_keys, hap_off, hap_key, hap_order, n_haps, (uint32_t)n_hb, t0, pd, n_dsts, dst_tile0);
+        else
+            transform_bits_gather_kernel<false><<<dim3((unsigned)(nt * n_hb)), kThreads, 0, (cudaStream_t)stream>>>(
+                planes, n_samples, n_keys, hap_off, hap_key, nullptr, n_haps, (uint32_t)n_hb, t0, pd, n_dsts, dst_tile0);
         HT_CUDA_TRY(cudaGetLastError());
     }
     return HT_OK;

@@ -136,15 +136,35 @@ class PeerGather:
         total_tiles = (self.n_samples + TILE - 1) // TILE
         self.bits = torch.as_tensor(_DevMem(self._own, (self.tiles, self.n_haps, 32, 2)), device=self.device)[:total_tiles]
 
-    def run(self, dplan, planes: torch.Tensor, n_local: int, stream=None) -> torch.Tensor:
+    @staticmethod
+    def key_order(dplan) -> torch.Tensor:
+        """Haplotypes by their first key (stable; haplotypes without alleles first): the order in which the kernel
+        computes them.  Cached on the DevicePlan."""
+        order = getattr(dplan, "_key_order", None)
+        if order is None:
+            plan = dplan.plan
+            off = plan.hap_off.astype(np.int64)
+            first = np.full(plan.n_haps, -1, dtype=np.int64)
+            has = off[1:] > off[:-1]
+            first[has] = plan.hap_key[off[:-1][has]]
+            order = torch.from_numpy(np.argsort(first, kind="stable").astype(np.int32)).to(dplan.hap_off.device)
+            dplan._key_order = order
+        return order
+
+    def run(self, dplan, planes: torch.Tensor, n_local: int, stream=None, ordered: bool = False) -> torch.Tensor:
         """This rank's shard (n_local samples, `shard_bounds`) -> its records in every rank's buffer; returns the
-        gathered tensor of THIS rank (complete when the stream has passed the closing all-reduce)."""
+        gathered tensor of THIS rank (complete when the stream has passed the closing all-reduce).  ordered: compute
+        the haplotypes in key order (the same records; neighbouring warps share their plane reads, but every warp
+        then stores its own 256-byte record instead of one 2 KB store per CTA: 11.4 against 10.5 ms at 2 GPUs, so
+        it is off by default)."""
         if n_local > self.per * TILE:
             raise ValueError("shard larger than shard_tiles(n_samples, world) tiles")
         st = stream or torch.cuda.current_stream(self.device)
+        order = self.key_order(dplan) if ordered and self.n_haps > 1 else None
         self._check(self.lib.ht_transform_bits_gather(
             planes.data_ptr() if planes is not None and planes.numel() else None, n_local, dplan.plan.n_keys,
-            dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr() if dplan.hap_key.numel() else None, self.n_haps,
+            dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr() if dplan.hap_key.numel() else None,
+            order.data_ptr() if order is not None else None, self.n_haps,
             self._dsts, self.world, self.rank * self.per, st.cuda_stream), "ht_transform_bits_gather")
         if self.world > 1:
             with torch.cuda.stream(st):

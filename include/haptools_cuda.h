@@ -250,11 +250,13 @@ int ht_transform_bits(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
  * NVLink / NVSwitch peer memory and overlaps the AND arithmetic record by record; what is left for the caller is a
  * barrier across ranks once the kernel has finished on all of them (haptools_b200.dist.PeerGather does it with a
  * stream-ordered one-element all-reduce).  n_dsts <= HT_MAX_PEERS.  With n_dsts == 1 and dst_tile0 == 0 it is
- * ht_transform_bits.
+ * ht_transform_bits.  hap_order (optional, device, n_haps entries: a permutation of 0 .. n_haps-1): the order in
+ * which the haplotypes are COMPUTED (the planner's key order makes neighbouring warps share plane lines); every
+ * record still lands at its haplotype's own position -- 256-byte records scatter for free.
  */
 #define HT_MAX_PEERS 16
 int ht_transform_bits_gather(const uint32_t* planes, int64_t n_samples, int64_t n_keys,
-                             const uint32_t* hap_off, const uint32_t* hap_key, int64_t n_haps,
+                             const uint32_t* hap_off, const uint32_t* hap_key, const uint32_t* hap_order, int64_t n_haps,
                              uint32_t* const* dsts, int32_t n_dsts, int64_t dst_tile0, void* stream);
 
 /*

@@ -38,6 +38,10 @@ def test_world_of_one_equals_transform_bits(n, H):
     try:
         bits = pg.run(dplan, planes, n)
         torch.cuda.synchronize()
+        first = bits.clone()
+        bits = pg.run(dplan, planes, n, ordered=True)  # haplotypes computed in key order: the same records
+        torch.cuda.synchronize()
+        assert torch.equal(bits, first)
         ref = torch.empty_like(bits)
         engine.transform_bits(dplan, planes, n, ref, method="direct")
         torch.cuda.synchronize()
@@ -56,19 +60,24 @@ def test_several_destinations_and_tile_offset():
     engine.transform_bits(dplan, planes, n, ref, method="direct")
     bufs = [torch.full((6, H, 32, 2), 0x5A5A5A5A, dtype=torch.int32, device="cuda") for _ in range(3)]
     dsts = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in bufs])
-    _cuda.check(lib.ht_transform_bits_gather(planes.data_ptr(), n, plan.n_keys, dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr(),
-                                             H, dsts, 3, 2, 0), "ht_transform_bits_gather")
-    torch.cuda.synchronize()
-    for b in bufs:
-        assert torch.equal(b[2:5], ref)
-        assert bool((b[:2] == 0x5A5A5A5A).all()) and bool((b[5:] == 0x5A5A5A5A).all())
+    order = hdist.PeerGather.key_order(dplan)
+    assert sorted(order.cpu().tolist()) == list(range(H))
+    for hap_order in (None, order.data_ptr()):  # caller order (one 2 KB bulk store per CTA) / key order (one per warp)
+        for b in bufs:
+            b.fill_(0x5A5A5A5A)
+        _cuda.check(lib.ht_transform_bits_gather(planes.data_ptr(), n, plan.n_keys, dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr(),
+                                                 hap_order, H, dsts, 3, 2, 0), "ht_transform_bits_gather")
+        torch.cuda.synchronize()
+        for b in bufs:
+            assert torch.equal(b[2:5], ref)
+            assert bool((b[:2] == 0x5A5A5A5A).all()) and bool((b[5:] == 0x5A5A5A5A).all())
     # argument errors
     assert lib.ht_transform_bits_gather(planes.data_ptr(), n, plan.n_keys, dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr(),
-                                        H, dsts, 0, 0, 0) == _cuda.HT_ERR_BAD_ARG
+                                        None, H, dsts, 0, 0, 0) == _cuda.HT_ERR_BAD_ARG
     assert lib.ht_transform_bits_gather(planes.data_ptr(), n, plan.n_keys, dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr(),
-                                        H, dsts, 17, 0, 0) == _cuda.HT_ERR_BAD_ARG
+                                        None, H, dsts, 17, 0, 0) == _cuda.HT_ERR_BAD_ARG
     assert lib.ht_transform_bits_gather(planes.data_ptr(), n, plan.n_keys, dplan.hap_off.data_ptr(), dplan.hap_key.data_ptr(),
-                                        H, dsts, 3, -1, 0) == _cuda.HT_ERR_BAD_ARG
+                                        None, H, dsts, 3, -1, 0) == _cuda.HT_ERR_BAD_ARG
 
 
 def test_two_processes_share_one_gpu():
