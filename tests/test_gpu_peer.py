@@ -82,9 +82,14 @@ def test_several_destinations_and_tile_offset():
 
 def test_two_processes_share_one_gpu():
     """Two ranks, CUDA IPC handles exchanged through the process group, each storing its shard into both buffers."""
+    import socket
+
     repo = Path(__file__).resolve().parent.parent
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=str(repo))
+    with socket.socket() as sock:  # a port nobody is using right now
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(repo / "tests" / "_peer_worker.py")]
+           "--master-port", str(port), str(repo / "tests" / "_peer_worker.py")]
     res = subprocess.run(cmd, env=env, cwd=str(repo), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert res.returncode == 0 and "PEER_GATHER_OK" in res.stdout, res.stdout[-3000:]
