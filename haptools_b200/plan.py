@@ -383,25 +383,49 @@ def plan_from_haplotypes(haps: Sequence, gts, ancestry: bool = False, who: str =
         ref_label = np.repeat(lab & 0xFF, lens)
     ids = [v.id for h in haps for v in h.variants]
     allele_strs = [v.allele for h in haps for v in h.variants]
-    if log is not None or n_distinct_out is not None:
-        n_distinct = len(set(zip(ids, allele_strs)))  # the reference's len(alleles), haplotypes.py:1387
-        if n_distinct_out is not None:
-            n_distinct_out.append(n_distinct)
-        if log is not None:
-            log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
+    want_count = log is not None or n_distinct_out is not None
+    logged = [0]
+
+    def log_lines(upto: int, n_distinct=None):
+        """The reference's two debug lines (haplotypes.py:1387, 1389), each once and in order.  `len(alleles)` there
+        counts distinct (variant ID, allele STRING) pairs: a set of 1.1 M pairs costs 0.1 s, so on the normal path
+        the count comes from the resolved (column, allele index) pairs instead (IDs are unique and `tuple.index`
+        is injective on a variant's alleles) -- except for the ancestry classes, whose index int(allele != REF)
+        is not."""
+        if logged[0] < 1 <= upto and want_count:
+            if n_distinct is None:
+                n_distinct = len(set(zip(ids, allele_strs)))
+            if n_distinct_out is not None:
+                n_distinct_out.append(n_distinct)
+            if log is not None:
+                log.debug(f"Copying genotypes for {n_distinct} distinct alleles")
+        if logged[0] < 2 <= upto and log is not None:
+            log.debug("Creating array denoting alt allele status")
+        logged[0] = max(logged[0], upto)
+
     gts.index(samples=False, variants=True)
     var_idx = gts._var_idx
     try:
         cols = np.fromiter(map(var_idx.__getitem__, ids), dtype=np.int64, count=len(ids))
     except KeyError:
+        log_lines(1)  # the reference logs its first line before it looks the variants up
         missing = [v for v in dict.fromkeys(ids) if v not in var_idx]
         raise ValueError(
             f"Variants {set(missing)} are present in {who or 'the haplotypes'} but absent in the provided genotypes"
         )
     var_alleles = gts.variants["alleles"] if len(ids) else ()
-    if log is not None:
-        log.debug("Creating array denoting alt allele status")
-    allele_idx = _allele_indices(var_alleles, cols, allele_strs, ancestry)
+    try:
+        allele_idx = _allele_indices(var_alleles, cols, allele_strs, ancestry)
+    except ValueError:
+        log_lines(2)  # both lines precede the reference's allele look-up
+        raise
+    n_distinct = None
+    if want_count and not ancestry and len(cols):
+        n_alleles = int(allele_idx.max()) + 1
+        n_distinct = len(np.unique(cols * n_alleles + allele_idx))
+    elif want_count and not len(cols):
+        n_distinct = 0
+    log_lines(2, n_distinct)
     if clip_bool and gts.data.dtype == np.bool_:
         # the reference builds allele_arr with dtype=bool (haplotypes.py:1398)
         allele_idx = np.minimum(allele_idx, 1)
