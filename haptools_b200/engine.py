@@ -589,17 +589,27 @@ class _HostPipe:
         self.regions = [None] * nbuf
         self.keep = []
         self.k = 0
+        self.uploads_queued = False
 
     def step(self) -> None:
         """Queue this device's next chunk; everything is asynchronous except the waits for host copy engine
         jobs whose buffers are needed again."""
         k = self.k
         self.k += 1
-        if k == 0:
-            self._start_upload(0)
-        if k + 1 < len(self.bounds):
-            self._start_upload(k + 1)  # flies while chunk k's kernels are queued
+        if not self.uploads_queued:
+            if k == 0:
+                self._start_upload(0)
+            if k + 1 < len(self.bounds):
+                self._start_upload(k + 1)  # flies while chunk k's kernels are queued
         self._compute(k)
+
+    def queue_all_uploads(self) -> None:
+        """With a buffer set per chunk every upload can be queued before the first kernel: the copy stream (or the
+        host copy engine, for a pageable source) then never waits for this thread to come back from a wait."""
+        if self.queues_everything and not self.uploads_queued:
+            for k in range(len(self.bounds)):
+                self._start_upload(k)
+            self.uploads_queued = True
 
     def _start_upload(self, k: int) -> None:
         b = k % self.nbuf
@@ -833,6 +843,8 @@ def transform_host(gt: np.ndarray, plan: TransformPlan, ancestry: np.ndarray = N
              for i, d in enumerate(devs)]
     # on_queued: called once, when this thread has no more than waiting left to do -- after the loop when every pipe
     # holds a buffer set per chunk (nothing in the loop waits then), else before it (the loop is most of the call)
+    for pp in pipes:
+        pp.queue_all_uploads()
     early = on_queued is not None and not all(pp.queues_everything and not pp.src_pageable for pp in pipes)
     if early:
         on_queued()
